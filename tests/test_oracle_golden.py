@@ -1,0 +1,140 @@
+"""Pin the oracle against fixtures produced by the reference's own functions
+(tests/golden/make_golden.py) and against cv2.findHomography.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+
+def _lc_case(g, i):
+    b, c, hs, ws, G, r, gb, nl, noflow = [int(v) for v in g[f"c{i}_meta"]]
+    mode, pad = [str(v) for v in g[f"c{i}_mode"]]
+    flow = None if noflow else torch.from_numpy(g[f"c{i}_flow"])
+    kw = dict(local_radius=r, num_grid=G, flow=flow, sample_mode=mode, padding_mode=pad,
+              grid_based_correlation=bool(gb), num_level=nl)
+    return (b, c, hs, ws), torch.from_numpy(g[f"c{i}_f0"]), torch.from_numpy(g[f"c{i}_f1"]), kw, torch.from_numpy(g[f"c{i}_out"])
+
+
+def test_local_correlation_port_and_def_match_reference(golden):
+    g = golden("local_correlation")
+    for i in range(int(g["ncases"])):
+        size, f0, f1, kw, ref = _lc_case(g, i)
+        port = oracle.local_correlation_port(size, f0, f1, **kw)
+        assert port.shape == ref.shape
+        torch.testing.assert_close(port, ref, rtol=1e-5, atol=1e-6)
+        d = oracle.local_correlation_def(size, f0, f1, **kw).float()
+        if kw["sample_mode"] == "nearest":
+            # rounding ties in fp32 coordinate arithmetic may pick another pixel; compare most entries
+            assert (torch.isclose(d, ref, rtol=1e-4, atol=1e-5)).float().mean() > 0.99
+        else:
+            torch.testing.assert_close(d, ref, rtol=1e-4, atol=2e-5)
+
+
+def test_coarse_match_matches_reference(golden):
+    g = golden("coarse_match")
+    for i in range(int(g["ncases"])):
+        f0, f1 = torch.from_numpy(g[f"c{i}_f0"]), torch.from_numpy(g[f"c{i}_f1"])
+        vol = oracle.corr_volume_port(f0, f1)
+        torch.testing.assert_close(vol, torch.from_numpy(g[f"c{i}_vol"]), rtol=1e-5, atol=1e-6)
+        flow = oracle.pos_embed_port(vol)
+        torch.testing.assert_close(flow, torch.from_numpy(g[f"c{i}_flow"]), rtol=1e-5, atol=1e-6)
+        d = oracle.coarse_match_def(f0, f1).float()
+        torch.testing.assert_close(d, torch.from_numpy(g[f"c{i}_flow"]), rtol=1e-4, atol=1e-5)
+
+
+def test_kde_matches_reference(golden):
+    g = golden("kde")
+    for i in range(int(g["ncases"])):
+        x = torch.from_numpy(g[f"c{i}_x"])
+        down = int(g[f"c{i}_down"])
+        down = None if down < 0 else down
+        ref = torch.from_numpy(g[f"c{i}_out"])
+        torch.testing.assert_close(oracle.kde_port(x, 0.1, half=False, down=down), ref, rtol=1e-6, atol=1e-6)
+        # the float64 definition agrees with the reference's fp32 cdist path to its own rounding
+        torch.testing.assert_close(oracle.kde_def(x, 0.1, down=down).float(), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_sample_matches_reference_with_same_generator(golden):
+    g = golden("sample")
+    warp, cert = torch.from_numpy(g["warp"]), torch.from_numpy(g["cert"])
+    num = int(g["num"])
+    torch.manual_seed(int(g["seed"]))
+    q1 = torch.empty(cert.numel()).exponential_(1)
+    q2 = torch.empty(min(4 * num, cert.numel())).exponential_(1)
+    gm, gc, idx1, idx2, rho = oracle.sample_port(warp, cert, num, q1, q2, half=False, down=8)
+    assert idx1.dtype == torch.int64 and idx2.dtype == torch.int64
+    assert torch.equal(gm, torch.from_numpy(g["good_matches"]))          # bit-exact selection + order
+    assert torch.equal(gc, torch.from_numpy(g["good_certainty"]))
+
+
+def test_multinomial_equivalence_cpu():
+    gen = torch.Generator().manual_seed(5)
+    p = torch.rand(5000, generator=gen)
+    p[p < 0.3] = 0.01
+    torch.manual_seed(11)
+    ref = torch.multinomial(p, 700, replacement=False)
+    torch.manual_seed(11)
+    q = torch.empty_like(p).exponential_(1)
+    assert torch.equal(oracle.multinomial_from_noise(p, q, 700), ref)
+
+
+def test_match_postprocess_shapes_and_rules():
+    gen = torch.Generator().manual_seed(3)
+    B, G = 2, 6
+    flow = torch.rand(2 * B, 2, G, G, generator=gen) * 2.4 - 1.2
+    logit = torch.randn(2 * B, 1, G, G, generator=gen)
+    warp, cert = oracle.match_postprocess_port(flow, logit, symmetric=True)
+    assert warp.shape == (B, G, 2 * G, 4) and cert.shape == (B, G, 2 * G)
+    assert warp.abs().max() <= 1
+    bad = (flow.abs() > 1).any(dim=1)                                   # [2B,G,G]
+    assert torch.all(cert[:, :, :G][bad[:B]] == 0) and torch.all(cert[:, :, G:][bad[B:]] == 0)
+    lat = oracle.sampling.lattice(G)
+    assert torch.equal(warp[0, :, :G, :2], lat) and torch.equal(warp[1, :, G:, 2:], lat)
+    torch.testing.assert_close(warp[0, :, :G, 2:], flow[0].permute(1, 2, 0).clamp(-1, 1))
+    torch.testing.assert_close(warp[1, :, G:, :2], flow[B + 1].permute(1, 2, 0).clamp(-1, 1))
+
+
+def test_estimation_restatement_against_cv2(golden):
+    g = golden("homography_cv2")
+    import cv2
+    for i in range(int(g["ncases"])):
+        pa, pb = g[f"c{i}_pa"], g[f"c{i}_pb"]
+        nout = int(g[f"c{i}_nout"])
+        # (1) DLT + refinement on a given point set == cv2.findHomography(method=0) on that set
+        H0, ok = oracle.weighted_dlt(pa[nout:], pb[nout:])
+        assert ok
+        H = oracle.refine_homography_lm(H0, pa[nout:], pb[nout:])
+        e = oracle.corner_error(H, g[f"c{i}_H_lsq_inliers"], 448, 448)
+        assert e < 1e-3, (i, e)
+        # (2) the same two stages on cv2's own RANSAC inlier mask reproduce cv2's RANSAC answer
+        m = g[f"c{i}_mask"].reshape(-1).astype(np.float64)
+        H1, ok = oracle.weighted_dlt(pa, pb, m)
+        H1 = oracle.refine_homography_lm(H1, pa, pb, m)
+        e = oracle.corner_error(H1, g[f"c{i}_H_ransac"], 448, 448)
+        assert e < 1e-3, (i, e)
+        # (3) installed cv2 still returns the recorded answer (version drift check)
+        if cv2.__version__ == str(g["cv2_version"]):
+            Hc, _, _ = oracle.find_homography_cv2(pa, pb)
+            assert np.allclose(Hc, g[f"c{i}_H_ransac"], rtol=1e-9, atol=1e-12)
+        # (4) the hash-sampled RANSAC restatement lands within 0.05 px of cv2 in these regimes
+        Hr, mask, ok = oracle.estimation.homography_ransac_def(pa, pb, seed=1, pair=i, nhyp=128)
+        assert ok
+        e = oracle.corner_error(Hr, g[f"c{i}_H_ransac"], 448, 448)
+        assert e < (0.01 if i < 2 else 0.2), (i, e)
+
+
+def test_corner_error_and_auc():
+    H = np.eye(3)
+    assert oracle.corner_error(H, H, 448, 448) == 0
+    assert oracle.corner_error(oracle.fallback_homography(), H, 448, 448) == 70.0
+    H2 = np.array([[1, 0, 3.0], [0, 1, 4.0], [0, 0, 1]])
+    assert abs(oracle.corner_error(H2, H, 448, 448) - 5.0) < 1e-12
+    a = oracle.auc([1.0, 2.0, 30.0], [3, 5, 10, 20])
+    ref_first = (0.5 * 1 * (1 / 3) + 1 * (1 / 3 + 2 / 3) * 0.5 + 1 * (2 / 3)) / 3   # trapezoid by hand
+    assert abs(a[0] - ref_first) < 1e-12 and a[0] < a[1] < a[2]
+
+
+def test_convert_coordinates():
+    a, b = oracle.convert_coordinates(np.array([[-1.0, 1.0]]), np.array([[0.0, 0.0]]), 448, 224, 560, 560)
+    assert np.allclose(a, [[0, 223]]) and np.allclose(b, [[279.5, 279.5]])
