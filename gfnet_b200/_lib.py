@@ -1,0 +1,96 @@
+"""ctypes binding of the C-ABI shared library (include/gfnet_b200.h).
+
+The product path has no fallback: if ``gfnet_b200/_C/libgfnet_b200.so`` is missing the import
+fails loudly with the build command.  PyTorch is used for device memory and streams only.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libgfnet_b200.so")
+
+EXPORTS = [
+    "gfb_abi_version", "gfb_strerror", "gfb_device_info", "gfb_local_corr_f32", "gfb_avg_pool2_f32",
+    "gfb_global_match_f32", "gfb_pos_embed_f32", "gfb_kde_f32", "gfb_match_postprocess_f32",
+    "gfb_sample_keys_f32", "gfb_balance_keys_f32", "gfb_gather_matches_f32", "gfb_topk_workspace_bytes",
+    "gfb_topk_desc_f32", "gfb_homography_workspace_bytes", "gfb_homography_f32", "gfb_corner_error_f64",
+]
+
+GFB_EINVAL, GFB_EUNSUPPORTED, GFB_EALIGN, GFB_EWORKSPACE, GFB_ENODEVICE = -1, -2, -3, -4, -5
+
+
+class GfbError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C gfnet_b200/csrc` "
+            "(needs nvcc >= 12.8, target sm_100a). gfnet_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, f32, i64, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_uint
+    sz = ctypes.c_size_t
+    lib.gfb_abi_version.restype = i32
+    lib.gfb_strerror.restype = ctypes.c_char_p
+    lib.gfb_strerror.argtypes = [i32]
+    lib.gfb_device_info.argtypes = [ctypes.POINTER(i32)] * 3
+    lib.gfb_local_corr_f32.argtypes = [vp, vp, vp, vp] + [i32] * 13 + [vp]
+    lib.gfb_avg_pool2_f32.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.gfb_global_match_f32.argtypes = [vp, vp, vp, vp] + [i32] * 8 + [vp]
+    lib.gfb_pos_embed_f32.argtypes = [vp, vp] + [i32] * 5 + [vp]
+    lib.gfb_kde_f32.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
+    lib.gfb_match_postprocess_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.gfb_sample_keys_f32.argtypes = [vp, vp, vp, i64, f32, vp]
+    lib.gfb_balance_keys_f32.argtypes = [vp, vp, vp, i64, f32, vp]
+    lib.gfb_gather_matches_f32.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, f32, vp]
+    lib.gfb_topk_workspace_bytes.restype = sz
+    lib.gfb_topk_workspace_bytes.argtypes = [i32, i64, i32]
+    lib.gfb_topk_desc_f32.argtypes = [vp, vp, i32, i64, i32, vp, sz, vp]
+    lib.gfb_homography_workspace_bytes.restype = sz
+    lib.gfb_homography_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.gfb_homography_f32.argtypes = [vp, vp, i32, i32, f32, f32, f32, f32, i32, f32, i32, u32, vp, vp, vp, vp, vp, sz, vp]
+    lib.gfb_corner_error_f64.argtypes = [vp, vp, vp, i32, f32, f32, f32, vp]
+    for name in EXPORTS:   # getattr raises AttributeError if the library lacks a declared symbol
+        if name not in ("gfb_strerror", "gfb_topk_workspace_bytes", "gfb_homography_workspace_bytes"):
+            getattr(lib, name).restype = i32
+    if lib.gfb_abi_version() != 1:
+        raise ImportError("libgfnet_b200.so ABI version mismatch; rebuild with `make -C gfnet_b200/csrc`")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what):
+    """0 -> ok; <0 -> ValueError / NotImplementedError (no fallback); >0 -> CUDA error."""
+    if rc == 0:
+        return
+    msg = f"{what}: {lib.gfb_strerror(rc).decode()} (code {rc})"
+    if rc == GFB_EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc < 0:
+        raise ValueError(msg)
+    raise GfbError(msg)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def stream_ptr(device=None):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda_f32(name, t, dtype=None):
+    import torch
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if t.device.type != "cuda":
+        raise RuntimeError(f"{name} is on {t.device}: gfnet_b200 runs on CUDA (sm_100a) only and has no CPU path")
+    want = dtype or torch.float32
+    if t.dtype != want:
+        raise TypeError(f"{name} must be {want}, got {t.dtype}")
+    return t.contiguous()

@@ -1,0 +1,501 @@
+// K1 -- local correlation (reference: utils/local_correlation.py:4-72, call site model/network.py:553).
+//
+// corr[b,k,gy,gx] = (1/sqrt C) sum_c f0[b,c,gy,gx] * bilinear(f1[b,c], flow[b,:,gy,gx] + off_k)
+//
+// Two kernels:
+//  * lc_generic_kernel  -- one thread per output element, direct gathers.  Mirrors the reference's
+//    coordinate arithmetic exactly (per-k fp32 `flow + offset`, unnormalise, floor) and covers every
+//    mode the reference can be called with that we support (bilinear/nearest, zeros/border,
+//    grid-based windows).  Slow path and in-kernel fallback.
+//  * lc_stream_kernel   -- the hot kernel.  Window offsets are whole pixels (linspace step 2/w is
+//    exactly one pixel under align_corners=False), so all K samples of a lattice point share one
+//    fractional part and corr = bilerp(D) with D[j,i] = sum_c f0[c] * f1[c, y0-r+j, x0-r+i] over a
+//    (2r+2)^2 integer patch.  A CTA owns a tile of lattice points; a producer warp streams the
+//    rows of f1 the tile touches through a shared-memory ring with TMA (box = BW x 1 row x CCH
+//    channels, out-of-image coordinates zero-filled by the TMA unit = padding_mode "zeros"); each
+//    consumer thread owns P vertically adjacent lattice points, keeps one D row per point in
+//    registers, reads a 128-bit-aligned superset segment of the f1 row once for its P points and
+//    emits the bilinear-combined outputs row by row with coalesced streaming stores.
+#include "common.cuh"
+#include <math.h>
+
+namespace gfb {
+
+struct LcParams {
+    const float* f0;
+    const float* f1;
+    const float* flow;
+    float* out;
+    int B, C, Hs, Ws, G, r;
+    int k_total, k_offset;
+    int sample_mode, padding_mode;
+    float ox0, ox1, oy0, oy1;  // torch.linspace endpoints of the window offsets (fp32)
+    float inv_sqrt_c;
+};
+
+// torch.linspace(start, end, steps)[i] in fp32 (ATen RangeFactories: symmetric evaluation).
+__device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
+    if (steps <= 1) return start;
+    float step = (end - start) / (float)(steps - 1);
+    return (i < steps / 2) ? start + step * (float)i : end - step * (float)(steps - 1 - i);
+}
+
+__device__ __forceinline__ float unnormalize(float c, int size) {  // align_corners = False
+    return ((c + 1.f) * (float)size - 1.f) / 2.f;
+}
+
+// One output element with the reference's exact per-sample coordinate arithmetic.
+__device__ float lc_generic_point(const LcParams& p, int b, int k, int gy, int gx) {
+    const int kw = 2 * p.r + 1;
+    const int iy = k / kw, ix = k - iy * kw;
+    const size_t gg = (size_t)p.G * p.G;
+    const float* fl = p.flow + (size_t)b * 2 * gg + (size_t)gy * p.G + gx;
+    float px = fl[0] + linspace_at(p.ox0, p.ox1, kw, ix);
+    float py = fl[gg] + linspace_at(p.oy0, p.oy1, kw, iy);
+    float sx = unnormalize(px, p.Ws), sy = unnormalize(py, p.Hs);
+    if (p.padding_mode == 1) {
+        sx = fminf((float)(p.Ws - 1), fmaxf(sx, 0.f));
+        sy = fminf((float)(p.Hs - 1), fmaxf(sy, 0.f));
+    }
+    const float* f0 = p.f0 + (size_t)b * p.C * gg + (size_t)gy * p.G + gx;
+    const float* f1 = p.f1 + (size_t)b * p.C * p.Hs * p.Ws;
+    const size_t plane = (size_t)p.Hs * p.Ws;
+    float acc = 0.f;
+    if (p.sample_mode == 1) {
+        float rx = rintf(sx), ry = rintf(sy);
+        if (rx >= 0.f && rx < (float)p.Ws && ry >= 0.f && ry < (float)p.Hs) {
+            size_t o = (size_t)(int)ry * p.Ws + (int)rx;
+            for (int c = 0; c < p.C; ++c) acc = fmaf(f0[c * gg], f1[c * plane + o], acc);
+        }
+        return acc * p.inv_sqrt_c;
+    }
+    if (!(fabsf(sx) < 1e8f) || !(fabsf(sy) < 1e8f)) return 0.f;  // far outside / non-finite: all taps out
+    float x0f = floorf(sx), y0f = floorf(sy);
+    int x0 = (int)x0f, y0 = (int)y0f;
+    float tx = sx - x0f, ty = sy - y0f;
+    float w00 = (1.f - tx) * (1.f - ty), w01 = tx * (1.f - ty), w10 = (1.f - tx) * ty, w11 = tx * ty;
+    bool xa = x0 >= 0 && x0 < p.Ws, xb = x0 + 1 >= 0 && x0 + 1 < p.Ws;
+    bool ya = y0 >= 0 && y0 < p.Hs, yb = y0 + 1 >= 0 && y0 + 1 < p.Hs;
+    if (!xa) { w00 = 0.f; w10 = 0.f; }
+    if (!xb) { w01 = 0.f; w11 = 0.f; }
+    if (!ya) { w00 = 0.f; w01 = 0.f; }
+    if (!yb) { w10 = 0.f; w11 = 0.f; }
+    int xc0 = min(max(x0, 0), p.Ws - 1), xc1 = min(max(x0 + 1, 0), p.Ws - 1);
+    int yc0 = min(max(y0, 0), p.Hs - 1), yc1 = min(max(y0 + 1, 0), p.Hs - 1);
+    size_t o00 = (size_t)yc0 * p.Ws + xc0, o01 = (size_t)yc0 * p.Ws + xc1;
+    size_t o10 = (size_t)yc1 * p.Ws + xc0, o11 = (size_t)yc1 * p.Ws + xc1;
+    for (int c = 0; c < p.C; ++c) {
+        const float* q = f1 + c * plane;
+        float s = w00 * __ldg(q + o00) + w01 * __ldg(q + o01) + w10 * __ldg(q + o10) + w11 * __ldg(q + o11);
+        acc = fmaf(__ldg(f0 + c * gg), s, acc);
+    }
+    return acc * p.inv_sqrt_c;
+}
+
+__global__ void __launch_bounds__(256) lc_generic_kernel(LcParams p) {
+    const int kk = (2 * p.r + 1) * (2 * p.r + 1);
+    const size_t gg = (size_t)p.G * p.G;
+    const size_t total = (size_t)p.B * kk * gg;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        int gx = (int)(t % p.G);
+        int gy = (int)((t / p.G) % p.G);
+        int k = (int)((t / gg) % kk);
+        int b = (int)(t / (gg * kk));
+        p.out[((size_t)b * p.k_total + p.k_offset + k) * gg + (size_t)gy * p.G + gx] = lc_generic_point(p, b, k, gy, gx);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hot kernel.
+//   CCH  channels per shared-memory stage (C must be a multiple; C == CCH lets f0 live in registers)
+//   R    window radius; W = 2R+2 columns/rows of the integer patch D, KW = 2R+1 outputs per row
+//   P    vertically adjacent lattice points per thread (share one f1 segment load)
+//   WP   padded segment width in floats (multiple of 4): W + alignment + shear slack
+//   F0REG keep the thread's f0 vectors in registers (needs C == CCH and CCH*P <= 64)
+struct LcTile {
+    int TR, TC;    // lattice rows / cols per CTA tile (TR = P * NBR)
+    int BW;        // smem row width in floats (multiple of 4, <= 256)
+    int NST;       // ring stages
+    int NCW;       // consumer warps
+};
+
+template <int CCH, int R, int P, int WP, bool F0REG>
+__global__ void __launch_bounds__(P >= 4 ? 224 : 352, 1)
+lc_stream_kernel(const LcParams p, const LcTile t, const __grid_constant__ CUtensorMap tmap_f1) {
+    constexpr int W = 2 * R + 2;
+    constexpr int KW = 2 * R + 1;
+    constexpr int SHMAX = WP - W;
+    static_assert(WP % 4 == 0 && SHMAX >= 3 && SHMAX <= 15, "segment must cover any 16B misalignment");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    const int stage_floats = CCH * t.BW;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)t.NST * stage_floats * sizeof(float));
+    uint64_t* empty_bar = full_bar + t.NST;
+    __shared__ int s_red[6];  // xmin, xmax, ymin, ymax, overflow, live
+
+    const int G = p.G;
+    const int tiles_x = (G + t.TC - 1) / t.TC, tiles_y = (G + t.TR - 1) / t.TR;
+    int tile = blockIdx.x;
+    const int tcx = tile % tiles_x; tile /= tiles_x;
+    const int tcy = tile % tiles_y;
+    const int b = tile / tiles_y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool is_consumer = warp < t.NCW;
+    const int NBR = t.TR / P;
+    const size_t gg = (size_t)G * G;
+
+    if (threadIdx.x == 0) {
+        s_red[0] = INT_MAX; s_red[1] = INT_MIN; s_red[2] = INT_MAX; s_red[3] = INT_MIN; s_red[4] = 0; s_red[5] = 0;
+        for (int s = 0; s < t.NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], t.NCW); }
+        mbar_fence_init();
+    }
+    if (warp == t.NCW && lane == 0) tma_prefetch_desc(&tmap_f1);
+
+    // ---- per-thread point setup -------------------------------------------------------------
+    const int tid = threadIdx.x;
+    const bool has_pts = is_consumer && tid < NBR * t.TC;
+    const int rg = has_pts ? tid / t.TC : 0;
+    const int gx = tcx * t.TC + (has_pts ? tid % t.TC : 0);
+    int yb[P], sh[P];
+    float wx1[P], wy0[P], wy1[P];
+    bool valid[P], dead[P];
+    int basex = INT_MAX;
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const int gy = tcy * t.TR + rg * P + q;
+        valid[q] = has_pts && gy < G && gx < G;
+        dead[q] = true; yb[q] = 0; sh[q] = 0; wx1[q] = 0.f; wy0[q] = 0.f; wy1[q] = 0.f;
+        if (valid[q]) {
+            const float* fl = p.flow + (size_t)b * 2 * gg + (size_t)gy * G + gx;
+            float sx = unnormalize(__ldg(fl), p.Ws), sy = unnormalize(__ldg(fl + gg), p.Hs);
+            if (fabsf(sx) < 1e6f && fabsf(sy) < 1e6f) {
+                float x0f = floorf(sx), y0f = floorf(sy);
+                int xb = (int)x0f - R;
+                yb[q] = (int)y0f - R;
+                float tx = sx - x0f, ty = sy - y0f;
+                wx1[q] = tx;
+                wy0[q] = (1.f - ty) * p.inv_sqrt_c;
+                wy1[q] = ty * p.inv_sqrt_c;
+                dead[q] = (xb >= p.Ws) || (xb + W <= 0) || (yb[q] >= p.Hs) || (yb[q] + W <= 0);
+                sh[q] = xb;  // absolute for now
+                if (!dead[q]) basex = min(basex, xb);
+            }
+        }
+    }
+    bool any_live = basex != INT_MAX;
+    bool overflow = false;
+    int ymin = INT_MAX, ymax = INT_MIN;
+    if (any_live) {
+        basex &= ~3;  // floor to a 16-byte boundary (two's complement: works for negatives)
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            if (!dead[q]) {
+                sh[q] -= basex;
+                overflow |= sh[q] > SHMAX;
+                ymin = min(ymin, yb[q]);
+                ymax = max(ymax, yb[q] + W);
+            }
+        }
+    } else {
+        basex = 0;
+    }
+    __syncthreads();  // s_red + barriers initialised
+    {
+        int xmn = warp_min(any_live ? basex : INT_MAX), xmx = warp_max(any_live ? basex + WP : INT_MIN);
+        int ymn = warp_min(ymin), ymx = warp_max(ymax);
+        unsigned ov = __ballot_sync(0xffffffffu, overflow), lv = __ballot_sync(0xffffffffu, any_live);
+        if (lane == 0 && lv) {
+            atomicMin(&s_red[0], xmn); atomicMax(&s_red[1], xmx);
+            atomicMin(&s_red[2], ymn); atomicMax(&s_red[3], ymx);
+            if (ov) atomicOr(&s_red[4], 1);
+            atomicOr(&s_red[5], 1);
+        }
+    }
+    __syncthreads();
+    const bool tile_live = s_red[5] != 0;
+    const int xbox0 = s_red[0] & ~3;
+    const int ylo = s_red[2], yhi = s_red[3];
+    const bool tile_overflow = tile_live && (s_red[4] != 0 || s_red[1] - xbox0 > t.BW);
+
+    float* outb = p.out + ((size_t)b * p.k_total + p.k_offset) * gg;
+
+    if (!tile_live || tile_overflow) {
+        // dead tile -> zeros; overflowing tile (window spread wider than the staged box or shear
+        // beyond the segment slack) -> exact per-sample gathers.
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            if (!valid[q]) continue;
+            const int gy = tcy * t.TR + rg * P + q;
+            float* o = outb + (size_t)gy * G + gx;
+            for (int k = 0; k < KW * KW; ++k)
+                st_stream(o + (size_t)k * gg, tile_live ? lc_generic_point(p, b, k, gy, gx) : 0.f);
+        }
+        return;
+    }
+
+    const int nchunk = p.C / CCH;
+    // ---- producer warp: stream rows [ylo, yhi) ∩ [0, Hs) x channel chunks through the ring -----
+    if (!is_consumer) {
+        if (warp == t.NCW && lane == 0) {
+            const uint32_t bytes = (uint32_t)stage_floats * sizeof(float);
+            int seq = 0;
+            for (int y = max(ylo, 0); y < min(yhi, p.Hs); ++y) {
+                for (int ch = 0; ch < nchunk; ++ch, ++seq) {
+                    const int s = seq % t.NST;
+                    if (seq >= t.NST) mbar_wait(&empty_bar[s], ((seq / t.NST) - 1) & 1);
+                    mbar_expect_tx(&full_bar[s], bytes);
+                    tma_load_3d(ring + (size_t)s * stage_floats, &tmap_f1, &full_bar[s], xbox0, y, b * p.C + ch * CCH);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumer threads ----------------------------------------------------------------------
+    float acc[P][WP], hprev[P][KW];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+#pragma unroll
+        for (int i = 0; i < WP; ++i) acc[q][i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < KW; ++i) hprev[q][i] = 0.f;
+    }
+    const float* f0p[P];
+    float f0r[F0REG ? P : 1][F0REG ? CCH : 1];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        const int gy = min(tcy * t.TR + rg * P + q, G - 1);
+        f0p[q] = p.f0 + (size_t)b * p.C * gg + (size_t)gy * G + min(gx, G - 1);
+        if (F0REG) {
+#pragma unroll
+            for (int c = 0; c < CCH; ++c) f0r[F0REG ? q : 0][F0REG ? c : 0] = (valid[q] && !dead[q]) ? __ldg(f0p[q] + (size_t)c * gg) : 0.f;
+        }
+    }
+    const int xoff = basex - xbox0;  // multiple of 4 floats
+    int seq = 0;
+    for (int y = ylo; y < yhi; ++y) {
+        bool act[P];
+        bool any_act = false;
+#pragma unroll
+        for (int q = 0; q < P; ++q) { act[q] = !dead[q] && (unsigned)(y - yb[q]) < (unsigned)W; any_act |= act[q]; }
+        const bool warp_act = __any_sync(0xffffffffu, any_act);
+        if ((unsigned)y < (unsigned)p.Hs) {
+            for (int ch = 0; ch < nchunk; ++ch, ++seq) {
+                const int s = seq % t.NST;
+                // every consumer warp waits on every stage (even rows it skips): that bounds how far
+                // a warp can run ahead and keeps its empty-barrier arrivals in the right phase
+                mbar_wait(&full_bar[s], (seq / t.NST) & 1);
+                if (warp_act) {
+                    if (any_act) {
+                        const float* srow = ring + (size_t)s * stage_floats + xoff;
+#pragma unroll (F0REG ? CCH : 2)
+                        for (int c = 0; c < CCH; ++c) {
+                            float seg[WP];
+#pragma unroll
+                            for (int v = 0; v < WP / 4; ++v) {
+                                float4 u = *reinterpret_cast<const float4*>(srow + c * t.BW + 4 * v);
+                                seg[4 * v] = u.x; seg[4 * v + 1] = u.y; seg[4 * v + 2] = u.z; seg[4 * v + 3] = u.w;
+                            }
+#pragma unroll
+                            for (int q = 0; q < P; ++q) {
+                                if (act[q]) {
+                                    const float f = F0REG ? f0r[F0REG ? q : 0][F0REG ? c : 0]
+                                                          : __ldg(f0p[q] + (size_t)(ch * CCH + c) * gg);
+#pragma unroll
+                                    for (int i = 0; i < WP; ++i) acc[q][i] = fmaf(f, seg[i], acc[q][i]);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+            }
+        }
+        // ---- finish D row j = y - yb for every active point: shift, lerp x, lerp y, store -----
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            if (!act[q]) continue;
+            const int j = y - yb[q];
+            if (SHMAX >= 8 && (sh[q] & 8)) {
+#pragma unroll
+                for (int i = 0; i + 8 < WP; ++i) acc[q][i] = acc[q][i + 8];
+            }
+            if (SHMAX >= 4 && (sh[q] & 4)) {
+#pragma unroll
+                for (int i = 0; i + 4 < WP; ++i) acc[q][i] = acc[q][i + 4];
+            }
+            if (sh[q] & 2) {
+#pragma unroll
+                for (int i = 0; i + 2 < WP; ++i) acc[q][i] = acc[q][i + 2];
+            }
+            if (sh[q] & 1) {
+#pragma unroll
+                for (int i = 0; i + 1 < WP; ++i) acc[q][i] = acc[q][i + 1];
+            }
+            const float a1 = wx1[q], a0 = 1.f - a1;
+            float* o = outb + ((size_t)(j - 1) * KW) * gg + (size_t)(tcy * t.TR + rg * P + q) * G + gx;
+#pragma unroll
+            for (int i = 0; i < KW; ++i) {
+                const float h = a0 * acc[q][i] + a1 * acc[q][i + 1];
+                if (j >= 1) st_stream(o + (size_t)i * gg, wy0[q] * hprev[q][i] + wy1[q] * h);
+                hprev[q][i] = h;
+            }
+#pragma unroll
+            for (int i = 0; i < WP; ++i) acc[q][i] = 0.f;
+        }
+    }
+    // lattice points whose whole window lies outside the image: zeros (padding_mode "zeros")
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        if (valid[q] && dead[q]) {
+            float* o = outb + (size_t)(tcy * t.TR + rg * P + q) * G + gx;
+            for (int k = 0; k < KW * KW; ++k) st_stream(o + (size_t)k * gg, 0.f);
+        }
+    }
+}
+
+__global__ void avg_pool2_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W) {
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t total = (size_t)N * Ho * Wo;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        int xo = (int)(t % Wo), yo = (int)((t / Wo) % Ho);
+        size_t n = t / ((size_t)Wo * Ho);
+        const float* q = x + n * H * W + (size_t)(2 * yo) * W + 2 * xo;
+        y[t] = (q[0] + q[1] + q[W] + q[W + 1]) * 0.25f;
+    }
+}
+
+template <int CCH, int R, int P, int WP, bool F0REG>
+static int launch_stream(const LcParams& p, cudaStream_t st) {
+    constexpr int W = 2 * R + 2;
+    LcTile t;
+    const int G = p.G;
+    // tile columns: whole lattice rows up to 80 wide, else the largest divisor-friendly width
+    if (G <= 80) t.TC = G;
+    else if (G % 64 == 0) t.TC = 64;
+    else if (G % 80 == 0) t.TC = 80;
+    else if (G % 48 == 0) t.TC = 48;
+    else t.TC = 64;
+    int NBR = max(1, min(8 / P, (P >= 4 ? 192 : 320) / t.TC));
+    t.TR = NBR * P;
+    t.NCW = (NBR * t.TC + 31) / 32;
+    const float s = (float)p.Ws / (float)G;
+    int bw_tile = (int)ceilf((float)t.TC * s * 1.35f) + WP + 8;
+    int bw_full = p.Ws + 2 * WP;
+    t.BW = ((min(bw_tile, bw_full) + 3) / 4) * 4;
+    if (t.BW > 256) return GFB_EUNSUPPORTED;
+    const size_t stage_bytes = (size_t)CCH * t.BW * sizeof(float);
+    t.NST = (int)min((size_t)6, (size_t)(200 * 1024) / stage_bytes);
+    if (t.NST < 2) return GFB_EUNSUPPORTED;
+    // keep two CTAs per SM resident when the ring allows it
+    if (t.NST > 4 && (size_t)t.NST * stage_bytes > 100 * 1024) t.NST = (int)max((size_t)3, (size_t)(100 * 1024) / stage_bytes);
+    const size_t smem = (size_t)t.NST * stage_bytes + 2 * t.NST * sizeof(uint64_t);
+
+    CUtensorMap tmap;
+    uint64_t dims[3] = {(uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B * p.C};
+    uint64_t strides[2] = {(uint64_t)p.Ws * 4, (uint64_t)p.Hs * p.Ws * 4};
+    uint32_t box[3] = {(uint32_t)t.BW, 1u, (uint32_t)CCH};
+    int rc = gfb_encode_tmap_f32(&tmap, p.f1, 3, dims, strides, box, 0);
+    if (rc != GFB_OK) return rc;
+
+    auto kern = lc_stream_kernel<CCH, R, P, WP, F0REG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int tiles = p.B * ((G + t.TR - 1) / t.TR) * ((G + t.TC - 1) / t.TC);
+    kern<<<tiles, (t.NCW + 1) * 32, smem, st>>>(p, t, tmap);
+    (void)W;
+    GFB_LAUNCH_RESULT();
+}
+
+}  // namespace gfb
+
+using namespace gfb;
+
+extern "C" int gfb_avg_pool2_f32(const float* x, float* y, int N, int H, int W, gfb_stream_t stream) {
+    GFB_CHECK_ARG(x && y && N > 0 && H >= 2 && W >= 2);
+    size_t total = (size_t)N * (H / 2) * (W / 2);
+    int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+    avg_pool2_kernel<<<blocks, 256, 0, gfb_cu(stream)>>>(x, y, N, H, W);
+    GFB_LAUNCH_RESULT();
+}
+
+extern "C" int gfb_local_corr_f32(const float* f0, const float* f1, const float* flow, float* out,
+                                  int B, int C, int Hs, int Ws, int G, int r,
+                                  int win_h, int win_w, int sample_mode, int padding_mode,
+                                  int k_total, int k_offset, int algo, gfb_stream_t stream) {
+    GFB_CHECK_ARG(f0 && f1 && flow && out);
+    GFB_CHECK_ARG(B > 0 && C > 0 && Hs > 0 && Ws > 0 && G > 0 && r >= 0 && win_h > 0 && win_w > 0);
+    GFB_CHECK_ARG(sample_mode == 0 || sample_mode == 1);
+    GFB_CHECK_ARG(padding_mode == 0 || padding_mode == 1);
+    const int kk = (2 * r + 1) * (2 * r + 1);
+    GFB_CHECK_ARG(k_offset >= 0 && k_offset + kk <= k_total);
+    GFB_CHECK_ARG(algo >= 0);
+    LcParams p;
+    p.f0 = f0; p.f1 = f1; p.flow = flow; p.out = out;
+    p.B = B; p.C = C; p.Hs = Hs; p.Ws = Ws; p.G = G; p.r = r;
+    p.k_total = k_total; p.k_offset = k_offset;
+    p.sample_mode = sample_mode; p.padding_mode = padding_mode;
+    // python: torch.linspace(-2*r/n, 2*r/n, 2r+1): endpoints are doubles rounded to fp32
+    p.ox0 = (float)(-2.0 * r / win_w); p.ox1 = (float)(2.0 * r / win_w);
+    p.oy0 = (float)(-2.0 * r / win_h); p.oy1 = (float)(2.0 * r / win_h);
+    p.inv_sqrt_c = (float)(1.0 / sqrt((double)C));
+    cudaStream_t st = gfb_cu(stream);
+
+    const bool stream_ok = win_h == Hs && win_w == Ws && sample_mode == 0 && padding_mode == 0 &&
+                           r >= 1 && r <= 8 && (Ws % 4 == 0) && gfb_aligned(f1, 16) &&
+                           (C % 16 == 0) && (size_t)B * C < (1ull << 31);
+    if (algo == 2 && !stream_ok) return GFB_EUNSUPPORTED;
+    if (algo != 1 && stream_ok) {
+        const int variant = algo >> 4;  // tuning knob: 0 = default table
+        int rc = GFB_EUNSUPPORTED;
+#define LC_CASE(CCH_, R_, P_, WP_, F0_) rc = launch_stream<CCH_, R_, P_, WP_, F0_>(p, st)
+        if (variant == 0 || variant == 2) {
+            if (C == 16) {
+                switch (r) {
+                    case 1: LC_CASE(16, 1, 2, 8, true); break;
+                    case 2: LC_CASE(16, 2, 2, 12, true); break;
+                    case 3: LC_CASE(16, 3, 2, 12, true); break;
+                    case 4: LC_CASE(16, 4, 2, 16, true); break;
+                    default: break;
+                }
+            } else if (C == 32) {
+                switch (r) {
+                    case 2: LC_CASE(32, 2, 2, 12, true); break;
+                    case 3: LC_CASE(32, 3, 2, 12, true); break;
+                    case 4: LC_CASE(32, 4, 2, 16, true); break;
+                    case 6: LC_CASE(32, 6, 2, 20, false); break;
+                    default: break;
+                }
+            } else if (C % 64 == 0) {
+                switch (r) {
+                    case 2: LC_CASE(64, 2, 2, 12, false); break;
+                    case 3: LC_CASE(64, 3, 2, 12, false); break;
+                    case 4: LC_CASE(64, 4, 2, 16, false); break;
+                    case 5: LC_CASE(64, 5, 2, 16, false); break;
+                    case 6: LC_CASE(64, 6, 2, 20, false); break;
+                    case 7: LC_CASE(64, 7, 2, 20, false); break;
+                    case 8: LC_CASE(64, 8, 2, 24, false); break;
+                    default: break;
+                }
+            }
+        } else if (variant == 1) {  // one point per thread
+            if (C == 16 && r == 2) LC_CASE(16, 2, 1, 12, true);
+            else if (C == 32 && r == 4) LC_CASE(32, 4, 1, 16, true);
+            else if (C % 64 == 0 && r == 6) LC_CASE(64, 6, 1, 20, false);
+            else if (C % 64 == 0 && r == 7) LC_CASE(64, 7, 1, 20, false);
+        } else if (variant == 4) {  // four points per thread
+            if (C == 16 && r == 2) LC_CASE(16, 2, 4, 12, true);
+            else if (C == 32 && r == 4) LC_CASE(32, 4, 4, 16, false);
+            else if (C % 64 == 0 && r == 6) LC_CASE(64, 6, 4, 20, false);
+            else if (C % 64 == 0 && r == 7) LC_CASE(64, 7, 4, 24, false);
+        }
+#undef LC_CASE
+        if (rc != GFB_EUNSUPPORTED || algo == 2 || (algo >> 4) != 0) return rc;
+    }
+    if (algo >= 2) return GFB_EUNSUPPORTED;
+    const size_t total = (size_t)B * kk * G * G;
+    int blocks = (int)min((size_t)148 * 32, (total + 255) / 256);
+    lc_generic_kernel<<<blocks, 256, 0, st>>>(p);
+    GFB_LAUNCH_RESULT();
+}

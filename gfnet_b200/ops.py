@@ -1,0 +1,175 @@
+"""Drop-in operators with the reference's Python signatures, backed by the sm_100a kernels.
+
+* ``local_correlation`` -- utils/local_correlation.py:4-16 (same positional/keyword arguments)
+* ``kde``               -- utils/kde.py:4
+* ``corr_volume`` / ``pos_embed`` / ``coarse_match`` -- GFNet.corr_volume / GFNet.pos_embed,
+  model/network.py:415-440
+
+CUDA fp32 tensors only.  Anything unsupported raises (ValueError / NotImplementedError): there is
+no CPU, PyTorch or Triton fallback.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, require_cuda_f32, stream_ptr
+
+_SAMPLE_MODES = {"bilinear": 0, "nearest": 1}
+_PADDING_MODES = {"zeros": 0, "border": 1}
+
+ALGO_AUTO, ALGO_GENERIC, ALGO_STREAM = 0, 1, 2
+
+
+def local_correlation(featuremap_size, feature0, feature1, local_radius, num_grid,
+                      padding_mode="zeros", flow=None, im_A_coords=None, sample_mode="bilinear",
+                      grid_based_correlation=False, num_level=1, *, algo=ALGO_AUTO, out=None):
+    """Flow-displaced (2r+1)^2 window correlation; reference: utils/local_correlation.py:4-72.
+
+    ``feature0 [B,c,G,G]``, ``feature1 [B,c,h,w]``, ``flow [B,2,G,G]`` (or None: identity lattice,
+    :21-30) -> ``corr [B, (2r+1)^2 * num_level, G, G]``, ``k = iy*(2r+1)+ix``.  ``im_A_coords`` is
+    accepted and ignored exactly as in the reference.
+    """
+    if sample_mode not in _SAMPLE_MODES:
+        raise NotImplementedError(f"sample_mode={sample_mode!r} (supported: bilinear, nearest)")
+    if padding_mode not in _PADDING_MODES:
+        raise NotImplementedError(f"padding_mode={padding_mode!r} (supported: zeros, border)")
+    B, c, h, w = (int(v) for v in featuremap_size)
+    f0 = require_cuda_f32("feature0", feature0)
+    f1 = require_cuda_f32("feature1", feature1)
+    G, r = int(num_grid), int(local_radius)
+    if f0.shape != (B, c, G, G):
+        raise ValueError(f"feature0 must be [B,c,num_grid,num_grid] = {(B, c, G, G)}, got {tuple(f0.shape)}")
+    if f1.dim() != 4 or f1.shape[0] != B or f1.shape[1] != c:
+        raise ValueError(f"feature1 must be [B,c,hs,ws] with B={B}, c={c}, got {tuple(f1.shape)}")
+    if flow is None:
+        if h * w != G * G:
+            raise ValueError("flow=None needs h*w == num_grid**2 (the reference reshapes the h x w lattice)")
+        ys = torch.linspace(-1 + 1 / h, 1 - 1 / h, h, device=f0.device)
+        xs = torch.linspace(-1 + 1 / w, 1 - 1 / w, w, device=f0.device)
+        gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+        flow = torch.stack((gx, gy), dim=0).reshape(1, 2, G, G).expand(B, 2, G, G)
+    fl = require_cuda_f32("flow", flow)
+    if fl.shape != (B, 2, G, G):
+        raise ValueError(f"flow must be [B,2,num_grid,num_grid], got {tuple(fl.shape)}")
+    kk = (2 * r + 1) ** 2
+    num_level = int(num_level)
+    if out is None:
+        out = torch.empty((B, kk * num_level, G, G), device=f0.device, dtype=f0.dtype)
+    elif out.shape != (B, kk * num_level, G, G) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("out has the wrong shape/layout")
+    win_h, win_w = (G, G) if grid_based_correlation else (h, w)
+    st = stream_ptr(f0.device)
+    with torch.cuda.device(f0.device):
+        for level in range(num_level):
+            hs, ws = int(f1.shape[2]), int(f1.shape[3])
+            rc = lib.gfb_local_corr_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, G, r, win_h, win_w,
+                                        _SAMPLE_MODES[sample_mode], _PADDING_MODES[padding_mode],
+                                        kk * num_level, kk * level, int(algo), st)
+            check(rc, "local_correlation")
+            if level + 1 < num_level:                      # local_correlation.py:71: avg_pool2d(2, 2)
+                nxt = torch.empty((B, c, hs // 2, ws // 2), device=f1.device, dtype=f1.dtype)
+                check(lib.gfb_avg_pool2_f32(ptr(f1), ptr(nxt), B * c, hs, ws, st), "avg_pool2")
+                f1 = nxt
+    return out
+
+
+def kde(x, std=0.1, half=True, down=None):
+    """Gaussian kernel density of the rows of ``x [M,D]`` (or batched ``[B,M,D]``).
+
+    reference: utils/kde.py:4-13.  Arithmetic is fp32 (the parity target is the reference's
+    ``half=False`` path).  ``half=True`` keeps the reference's dtype contract: the input is
+    rounded to fp16 first and an fp16 density is returned, but the sum itself is fp32.
+    """
+    if not isinstance(x, torch.Tensor) or x.device.type != "cuda":
+        raise RuntimeError("kde: x must be a CUDA tensor (no CPU path)")
+    xin = x.half().float() if half else x
+    xin = require_cuda_f32("x", xin if xin.dtype == torch.float32 else xin.float())
+    batched = xin.dim() == 3
+    if xin.dim() not in (2, 3):
+        raise ValueError("x must be [M,D] or [B,M,D]")
+    xb = xin if batched else xin[None]
+    B, M, D = (int(v) for v in xb.shape)
+    dens = torch.empty((B, M), device=xb.device, dtype=torch.float32)
+    with torch.cuda.device(xb.device):
+        rc = lib.gfb_kde_f32(ptr(xb), ptr(dens), B, M, D, 1 if down is None else int(down), float(std), stream_ptr(xb.device))
+    check(rc, "kde")
+    dens = dens if batched else dens[0]
+    return dens.half() if half else dens
+
+
+class LazyCorrVolume:
+    """What ``corr_volume`` returns: the two feature maps, so that ``pos_embed`` can run the fused
+    tensor-core kernel without the [B,H1,W1,H0,W0] volume ever touching HBM.  ``materialize()`` (or
+    any tensor-like use through ``.tensor``) produces the reference's volume."""
+
+    def __init__(self, feat0, feat1, precision):
+        self.feat0, self.feat1, self.precision = feat0, feat1, precision
+        B, C, H0, W0 = feat0.shape
+        _, _, H1, W1 = feat1.shape
+        self.shape = torch.Size((B, H1, W1, H0, W0))
+        self._tensor = None
+
+    def materialize(self):
+        if self._tensor is None:
+            _, self._tensor = _global_match(self.feat0, self.feat1, self.precision, want_volume=True)
+        return self._tensor
+
+    tensor = property(materialize)
+
+
+def _global_match(feat0, feat1, precision=0, want_volume=False, algo=0):
+    f0 = require_cuda_f32("feat0", feat0)
+    f1 = require_cuda_f32("feat1", feat1)
+    if f0.dim() != 4 or f1.dim() != 4 or f0.shape[:2] != f1.shape[:2]:
+        raise ValueError("feat0/feat1 must be [B,C,H,W] with equal B and C")
+    B, C, H0, W0 = (int(v) for v in f0.shape)
+    H1, W1 = int(f1.shape[2]), int(f1.shape[3])
+    flow = torch.empty((B, 2, H0, W0), device=f0.device, dtype=torch.float32)
+    vol = torch.empty((B, H1, W1, H0, W0), device=f0.device, dtype=torch.float32) if want_volume else None
+    with torch.cuda.device(f0.device):
+        rc = lib.gfb_global_match_f32(ptr(f0), ptr(f1), ptr(flow), ptr(vol), B, C, H0, W0, H1, W1,
+                                      int(precision), int(algo), stream_ptr(f0.device))
+    check(rc, "global_match")
+    return flow, vol
+
+
+def coarse_match(feat0, feat1, precision=0, algo=0):
+    """``pos_embed(corr_volume(feat0, feat1))`` fused; reference: model/network.py:251-252, 415-440.
+
+    ``precision`` 0 = 3xTF32 split (matches the reference's fp32 einsum to ~1e-6), 1 = one TF32 pass
+    (stated tolerance: |dflow| <= 5e-3 normalised on unit-variance features).
+    """
+    return _global_match(feat0, feat1, precision, False, algo)[0]
+
+
+def corr_volume(feat0, feat1, precision=0):
+    """GFNet.corr_volume (model/network.py:415-428); returns a lazy handle, see LazyCorrVolume."""
+    return LazyCorrVolume(feat0, feat1, precision)
+
+
+def pos_embed(corr):
+    """GFNet.pos_embed (model/network.py:430-440) on a LazyCorrVolume or a real [B,H1,W1,H0,W0] tensor."""
+    if isinstance(corr, LazyCorrVolume):
+        return coarse_match(corr.feat0, corr.feat1, corr.precision)
+    v = require_cuda_f32("corr_volume", corr)
+    if v.dim() != 5:
+        raise ValueError("corr_volume must be [B,H1,W1,H0,W0]")
+    B, H1, W1, H0, W0 = (int(s) for s in v.shape)
+    flow = torch.empty((B, 2, H0, W0), device=v.device, dtype=torch.float32)
+    with torch.cuda.device(v.device):
+        check(lib.gfb_pos_embed_f32(ptr(v), ptr(flow), B, H0, W0, H1, W1, stream_ptr(v.device)), "pos_embed")
+    return flow
+
+
+def local_correlation_bytes(B, c, hs, ws, G, r):
+    """Algorithmic HBM bytes of one call: read f0, f1, flow once, write corr once."""
+    return 4 * B * (c * G * G + c * hs * ws + 2 * G * G + (2 * r + 1) ** 2 * G * G)
+
+
+def global_match_flops(B, C, N0, N1):
+    return 2 * B * N0 * N1 * C
+
+
+__all__ = ["local_correlation", "kde", "coarse_match", "corr_volume", "pos_embed", "LazyCorrVolume",
+           "local_correlation_bytes", "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_STREAM"]

@@ -1,0 +1,52 @@
+"""The hot path end to end for a batch of pairs: global match -> local correlation at every scale /
+iteration / pass -> match post-process -> balanced sampling (kde) -> homography -> corner error.
+
+Order and shapes follow the reference's inference call stack: model/network.py:251-259
+(coarse match, refiner's local_correlation per scale), :326-349 (560 pass), :358-414 (post-process,
+sample), estimation.py:60-92 (H + metric).  The refiner's conv blocks between the local-correlation
+calls are out of scope, so each call gets its flow from the input batch.
+"""
+import torch
+
+from . import ops, matcher, estimation
+
+
+class HotPath:
+    def __init__(self, num_samples=5000, n_hyp=512, precision=0, lc_algo=0, seed=0):
+        self.num_samples, self.n_hyp, self.precision, self.lc_algo, self.seed = num_samples, n_hyp, precision, lc_algo, seed
+        self._corr = {}
+
+    def _corr_buf(self, key, shape, device):
+        buf = self._corr.get(key)
+        if buf is None or buf.shape != shape or buf.device != device:
+            buf = torch.empty(shape, device=device, dtype=torch.float32)
+            self._corr[key] = buf
+        return buf
+
+    def kernel_launches(self, batch):
+        """How many of our kernels one run() launches (bench.py's gpu_launches claim)."""
+        n = 1                                                   # global match
+        n += sum(len(sc["flows"]) for p in batch.passes for sc in p)   # local_corr
+        n += 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1                      # postprocess, keys, topk, gather, kde, balance, topk, gather
+        n += (2 if self.n_hyp > 0 else 0) + 1 + 1               # init+ransac, refit, corner error
+        return n
+
+    def run(self, batch, generator=None, noise=None):
+        out = {}
+        out["coarse_flow"] = ops.coarse_match(batch.coarse_f0, batch.coarse_f1, precision=self.precision)
+        for pi, scales in enumerate(batch.passes):
+            for sc in scales:
+                b, c, hs, G, r = sc["f1"].shape[0], sc["c"], sc["hs"], sc["G"], sc["r"]
+                for it, flow in enumerate(sc["flows"]):
+                    buf = self._corr_buf((pi, sc["scale"]), (b, (2 * r + 1) ** 2, G, G), flow.device)
+                    ops.local_correlation((b, c, hs, hs), sc["f0"], sc["f1"], r, G, flow=flow, algo=self.lc_algo, out=buf)
+        out["last_corr"] = buf
+        warp, cert = matcher.match_postprocess(batch.final_flow, batch.cert_logits, symmetric=True)
+        m, c = matcher.sample_batched(warp, cert, self.num_samples, generator=generator, noise=noise)
+        res = batch.res
+        H, status, ninl = estimation.estimate_homography(m, res, res, res, res, n_hyp=self.n_hyp, seed=self.seed)
+        err = estimation.corner_error(H, batch.H_gt, res, res)
+        out.update(H=H, status=status, n_inliers=ninl, err=err, matches=m)
+        # [B,12] result row: 9 H entries + error + inlier count + status (what the ranks gather)
+        out["result"] = torch.cat((H.reshape(-1, 9), err[:, None].double(), ninl[:, None].double(), status[:, None].double()), 1)
+        return out

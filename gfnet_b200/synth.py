@@ -1,0 +1,156 @@
+"""Seeded synthetic inputs of the hot path's shapes; data generation only.
+
+The backbone that produces the feature pyramid in the reference (DINOv2 + FPN, model/network.py:
+156-201) is out of scope, so the path is fed random-init pyramids whose correlations peak where a
+random homography says they should.  The random-H recipe mirrors the reference's 4-corner jitter
+(datasets/generate_random_H_large_size.py:6-36).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def pyramid_config(res=448, native=False, upsample_res=None):
+    """[(scale, c, hs, G, r)] coarse->fine for the scales that run local_correlation.
+
+    reference shapes: gfnet_configs/basic.json:20,23-26 (feat_chs [64,32,16,8], num_grid
+    [32,32,64,128,256], radius [7,6,4,2,0]); model/network.py:185-198; 560 pass: :326-349 (no scale 16).
+    """
+    chans = {16: 64, 8: 64, 4: 32, 2: 16}
+    radius = {16: 7, 8: 6, 4: 4, 2: 2}
+    out = []
+    if upsample_res is None:
+        g0 = res // 14
+        grids = {16: g0, 8: g0, 4: 2 * g0, 2: 4 * g0}
+        for s in (16, 8, 4, 2):
+            hs = res // 14 if s == 16 else res // s
+            out.append((s, chans[s], hs, grids[s], radius[s]))
+    else:
+        g0 = upsample_res // 14
+        grids = {8: g0, 4: 2 * g0, 2: 4 * g0}
+        for s in (8, 4, 2):
+            out.append((s, chans[s], upsample_res // s, grids[s], radius[s]))
+    return out
+
+
+def final_grid(res=448, upsample_res=560):
+    return 8 * ((upsample_res if upsample_res else res) // 14)
+
+
+def solve_h4(src, dst):
+    A = np.zeros((8, 8)); b = np.zeros(8)
+    for i in range(4):
+        X, Y = src[i]; x, y = dst[i]
+        A[2 * i] = [X, Y, 1, 0, 0, 0, -x * X, -x * Y]; b[2 * i] = x
+        A[2 * i + 1] = [0, 0, 0, X, Y, 1, -y * X, -y * Y]; b[2 * i + 1] = y
+    return np.concatenate((np.linalg.solve(A, b), [1.0])).reshape(3, 3)
+
+
+def random_homography(gen, jitter=0.15):
+    """Normalised-coordinate H: the 4 corners of [-1,1]^2 moved by U(-jitter, jitter) * 2."""
+    src = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], dtype=np.float64)
+    d = (torch.rand(4, 2, generator=gen, dtype=torch.float64).numpy() * 2 - 1) * (2 * jitter)
+    return solve_h4(src, src + d)
+
+
+def to_pixel_homography(Hn, wq, hq, wsup, hsup):
+    """Same map between pixel frames under estimation.py:26-45's convention px = (w-1)(x+1)/2."""
+    Ta = np.array([[(wq - 1) / 2, 0, (wq - 1) / 2], [0, (hq - 1) / 2, (hq - 1) / 2], [0, 0, 1.0]])
+    Tb = np.array([[(wsup - 1) / 2, 0, (wsup - 1) / 2], [0, (hsup - 1) / 2, (hsup - 1) / 2], [0, 0, 1.0]])
+    return Tb @ Hn @ np.linalg.inv(Ta)
+
+
+def lattice(g, device="cpu"):
+    t = torch.linspace(-1 + 1 / g, 1 - 1 / g, g, device=device)
+    yy, xx = torch.meshgrid(t, t, indexing="ij")
+    return torch.stack((xx, yy), 0)                      # [2,G,G] (x,y)
+
+
+def warp_points(H, pts):
+    """pts [2,...] normalised -> H applied, same shape (H: 3x3 tensor)."""
+    x, y = pts[0], pts[1]
+    d = H[2, 0] * x + H[2, 1] * y + H[2, 2]
+    return torch.stack(((H[0, 0] * x + H[0, 1] * y + H[0, 2]) / d, (H[1, 0] * x + H[1, 1] * y + H[1, 2]) / d), 0)
+
+
+def homography_flow(Hs, g, hs, gen, device, jitter_px=0.5):
+    """flow [b,2,G,G]: lattice warped by each H plus N(0, (jitter_px * 2/hs)^2)."""
+    lat = lattice(g, device)
+    out = []
+    for H in Hs:
+        Ht = torch.as_tensor(H, dtype=torch.float32, device=device)
+        out.append(warp_points(Ht, lat))
+    fl = torch.stack(out)
+    if jitter_px:
+        fl = fl + torch.randn(fl.shape, generator=gen, device=device) * (jitter_px * 2 / hs)
+    return fl.float().contiguous()
+
+
+def scale_inputs(Hs, c, hs, g, gen, device, correlated=True, adversarial=False):
+    """(feature0 [b,c,G,G], feature1 [b,c,hs,hs], flow [b,2,G,G]) for one scale."""
+    b = len(Hs)
+    f1 = torch.randn((b, c, hs, hs), generator=gen, device=device)
+    if adversarial:
+        flow = (torch.rand((b, 2, g, g), generator=gen, device=device) * 2.4 - 1.2)
+    else:
+        flow = homography_flow(Hs, g, hs, gen, device)
+    if correlated:
+        f0 = F.grid_sample(f1, flow.permute(0, 2, 3, 1), mode="bilinear", align_corners=False)
+        f0 = f0 + 0.5 * torch.randn(f0.shape, generator=gen, device=device)
+    else:
+        f0 = torch.randn((b, c, g, g), generator=gen, device=device)
+    return f0.contiguous(), f1.contiguous(), flow.contiguous()
+
+
+def make_matches(H, m, gen, device, sigma=0.002, outlier_frac=0.0):
+    """[m,4] normalised matches a -> H(a) + noise; a ~ U(-1,1)^2."""
+    a = torch.rand((m, 2), generator=gen, device=device) * 2 - 1
+    Ht = torch.as_tensor(H, dtype=torch.float32, device=device)
+    bq = warp_points(Ht, a.T).T + torch.randn((m, 2), generator=gen, device=device) * sigma
+    nout = int(outlier_frac * m)
+    if nout:
+        bq[:nout] = torch.rand((nout, 2), generator=gen, device=device) * 2 - 1
+    return torch.cat((a, bq), 1).float().contiguous()
+
+
+class PairBatch:
+    """All tensors one step of the hot path consumes for B pairs (symmetric => op batch b = 2B)."""
+
+    def __init__(self, B, res=448, upsample_res=560, num_itr=1, seed=1234, device="cuda", rank=0,
+                 pair_offset=0, native=False):
+        self.B, self.res, self.upsample_res, self.num_itr = B, res, upsample_res, num_itr
+        dev = torch.device(device)
+        gen = torch.Generator(device=dev).manual_seed(seed + 1000 * rank + pair_offset)
+        cgen = torch.Generator().manual_seed(seed + 1000 * rank + pair_offset)
+        self.Hn = [random_homography(cgen) for _ in range(B)]
+        Hs = self.Hn + [np.linalg.inv(h) for h in self.Hn]            # A->B then B->A (network.py:213-222)
+        self.H_gt = torch.as_tensor(np.stack([to_pixel_homography(h, res, res, res, res) for h in self.Hn]),
+                                    dtype=torch.float64, device=dev)
+        self.passes = []
+        for up in ([None, upsample_res] if upsample_res else [None]):
+            scales = []
+            for (s, c, hs, g, r) in pyramid_config(res, native, up):
+                f0, f1, _ = scale_inputs(Hs, c, hs, g, gen, dev)
+                flows = [homography_flow(Hs, g, hs, gen, dev) for _ in range(num_itr)]
+                scales.append(dict(scale=s, c=c, hs=hs, G=g, r=r, f0=f0, f1=f1, flows=flows))
+            self.passes.append(scales)
+        # coarse features for the global match: the scale-16 maps of pass 1 (full f0 map = grid features there)
+        s16 = self.passes[0][0]
+        self.coarse_f0, self.coarse_f1 = s16["f0"], s16["f1"]
+        G = final_grid(res, upsample_res)
+        self.G = G
+        self.final_flow = homography_flow(Hs, G, G, gen, dev, jitter_px=0.25)
+        self.cert_logits = (torch.randn((2 * B, 1, G, G), generator=gen, device=dev) * 2 + 1).contiguous()
+
+    def tensors(self):
+        out = [self.coarse_f0, self.coarse_f1, self.final_flow, self.cert_logits, self.H_gt]
+        for scales in self.passes:
+            for sc in scales:
+                out += [sc["f0"], sc["f1"]] + sc["flows"]
+        seen, uniq = set(), []
+        for t in out:
+            if t.data_ptr() not in seen:
+                seen.add(t.data_ptr()); uniq.append(t)
+        return uniq

@@ -1,0 +1,141 @@
+/*
+ * gfnet_b200 -- C ABI of the B200-native GFNet hot path (dense matching + homography).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every pointer is a
+ * DEVICE pointer unless said otherwise; tensors are contiguous in the stated layout; `stream` is
+ * a cudaStream_t (0 = legacy default stream).  The library never allocates device memory, never
+ * synchronises the device and never touches a stream other than the one passed.  All entry
+ * points are re-entrant (no mutable global state except an immutable driver-entry-point cache).
+ *
+ * Return convention: 0 = OK, <0 = GFB_E* (bad/unsupported argument, nothing launched),
+ * >0 = the cudaError_t of the failed launch.  `gfb_strerror` explains both.
+ *
+ * Each function cites the reference interface (KN-Zhang/GFNet @ 2281c4b) it replaces.
+ */
+#ifndef GFNET_B200_H
+#define GFNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFB_ABI_VERSION 1
+
+#define GFB_OK 0
+#define GFB_EINVAL (-1)       /* bad shape / null pointer / bad enum          */
+#define GFB_EUNSUPPORTED (-2) /* valid in the reference, not implemented here */
+#define GFB_EALIGN (-3)       /* pointer not aligned as required              */
+#define GFB_EWORKSPACE (-4)   /* workspace too small                          */
+#define GFB_ENODEVICE (-5)    /* no sm_100 device / driver entry point missing */
+
+typedef void* gfb_stream_t; /* cudaStream_t */
+
+int gfb_abi_version(void);
+const char* gfb_strerror(int code);
+/* sm count and compute capability of the current device (host-side query). */
+int gfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: local correlation --------------------------------------------------------------
+ * replaces utils/local_correlation.py:4-72 `local_correlation(featuremap_size, feature0,
+ * feature1, local_radius, num_grid, padding_mode, flow, im_A_coords, sample_mode,
+ * grid_based_correlation, num_level)`; call site model/network.py:553-554.
+ *   f0   [B,C,G,G]   grid features of image A        (fp32, NCHW)
+ *   f1   [B,C,Hs,Ws] feature map of image B          (fp32, NCHW)
+ *   flow [B,2,G,G]   normalised (x,y) targets in B   (fp32; ch0 = x, ch1 = y)
+ *   out  [B,Ktot,G,G]; this call writes channels [k_offset, k_offset + (2r+1)^2)
+ *        out[b, k_offset + iy*(2r+1)+ix, gy, gx] =
+ *            (1/sqrt(C)) * sum_c f0[b,c,gy,gx] * sample(f1[b,c], flow[b,:,gy,gx] + off(ix,iy))
+ *   off(ix,iy) = ((ix-r)*2/win_w, (iy-r)*2/win_h) built like torch.linspace(-2r/n, 2r/n, 2r+1);
+ *        win_w/win_h = (Ws,Hs) of `featuremap_size` normally, or num_grid when
+ *        grid_based_correlation=True (local_correlation.py:33-52).
+ *   sample_mode 0 = bilinear, 1 = nearest; padding_mode 0 = zeros, 1 = border; align_corners=False.
+ *   algo 0 = auto, 1 = generic gather kernel, 2 = TMA row-streaming kernel (requires
+ *        win == (Ws,Hs), bilinear, zeros, C in {8,16,32,64}, 1 <= r <= 8, Ws % 4 == 0).
+ * num_level > 1 (local_correlation.py:61-71) = one call per level with `gfb_avg_pool2_f32` between. */
+int gfb_local_corr_f32(const float* f0, const float* f1, const float* flow, float* out,
+                       int B, int C, int Hs, int Ws, int G, int r,
+                       int win_h, int win_w, int sample_mode, int padding_mode,
+                       int k_total, int k_offset, int algo, gfb_stream_t stream);
+/* F.avg_pool2d(x, 2, 2) on [N,H,W] planes -> [N,H/2,W/2] (local_correlation.py:71). */
+int gfb_avg_pool2_f32(const float* x, float* y, int N, int H, int W, gfb_stream_t stream);
+
+/* ---- K2: coarse global match --------------------------------------------------------------
+ * replaces GFNet.corr_volume + GFNet.pos_embed, model/network.py:415-440 (call site :251-252).
+ *   f0 [B,C,H0,W0], f1 [B,C,H1,W1] fp32 NCHW
+ *   flow_out [B,2,H0,W0]: softmax over the N1 = H1*W1 positions of image B of
+ *        <f0[:,i], f1[:,j]>/sqrt(C), then expectation of grid[j] = (-1+(2x+1)/W1, -1+(2y+1)/H1)
+ *   vol_out  [B,N1,N0] (= the reference's [B,H1,W1,H0,W0]) or NULL to skip materialising it
+ *   precision 0 = 3xTF32 split (fp32-faithful), 1 = single TF32 pass; tcgen05 tensor cores.
+ *   algo 0 = auto (tcgen05), 1 = SIMT fp32 kernel (any C), 2 = tcgen05 (C % 8 == 0, C <= 128). */
+int gfb_global_match_f32(const float* f0, const float* f1, float* flow_out, float* vol_out,
+                         int B, int C, int H0, int W0, int H1, int W1,
+                         int precision, int algo, gfb_stream_t stream);
+
+/* GFNet.pos_embed on a materialised volume vol [B,N1,N0] (model/network.py:430-440). */
+int gfb_pos_embed_f32(const float* vol, float* flow_out, int B, int H0, int W0, int H1, int W1,
+                      gfb_stream_t stream);
+
+/* ---- K3: kernel density ---------------------------------------------------------------------
+ * replaces utils/kde.py:4-13 `kde(x, std, half, down)`; call site model/network.py:406-408.
+ *   x [B,M,D] fp32 (D <= 8; the path uses D = 4), density [B,M]
+ *   density[b,m] = sum_{m' = 0, down, 2*down, ...} exp(-||x[b,m]-x[b,m']||^2 / (2 std^2))
+ * fp32 throughout (the parity target is the reference's half=False path). */
+int gfb_kde_f32(const float* x, float* density, int B, int M, int D, int down, float std,
+                gfb_stream_t stream);
+
+/* ---- match post-process (tail of GFNet.match, model/network.py:358-384) -----------------------
+ *   flow [b,2,G,G], cert_logits [b,1,G,G], attenuation [b,1,G,G] or NULL (the low_res_certainty
+ *   term, :334-340, already upsampled).  symmetric != 0: b = 2*Bp, A->B maps first, output
+ *   warp [Bp,G,2G,4], cert [Bp,G,2G]; else warp [b,G,G,4], cert [b,G,G]. */
+int gfb_match_postprocess_f32(const float* flow, const float* cert_logits, const float* attenuation,
+                              float* warp, float* cert, int b, int G, int symmetric,
+                              gfb_stream_t stream);
+
+/* ---- balanced sampling pieces (GFNet.sample, model/network.py:385-414) ------------------------
+ * torch.multinomial(p, n, replacement=False) == topk(p / q, n), q ~ Exp(1) (ATen); the Exp(1)
+ * draw stays with the caller's generator, these kernels do everything around it.
+ *   gfb_sample_keys_f32:   key[i] = (cert[i] > thresh ? 1 : cert[i]) / noise[i]      (:391-394,:400)
+ *   gfb_balance_keys_f32:  p = 1/(rho+1), p[rho < min_density] = 1e-7; key = p/noise  (:409-411)
+ *   gfb_gather_matches_f32: out_m[b,i,:] = warp[b, idx[b,i], :], out_c[b,i] = thresholded cert
+ *   gfb_topk_desc_f32: per row of keys [B,n], the k largest in descending order (ties: lower
+ *        index first), int64 indices like torch.topk; workspace from gfb_topk_workspace_bytes. */
+int gfb_sample_keys_f32(const float* cert, const float* noise, float* key, long long n, float thresh,
+                        gfb_stream_t stream);
+int gfb_balance_keys_f32(const float* density, const float* noise, float* key, long long n,
+                         float min_density, gfb_stream_t stream);
+int gfb_gather_matches_f32(const float* warp, const float* cert, const int64_t* idx,
+                           float* out_m, float* out_c, int B, long long n_src, int n_sel,
+                           float thresh, gfb_stream_t stream);
+size_t gfb_topk_workspace_bytes(int B, long long n, int k);
+int gfb_topk_desc_f32(const float* keys, int64_t* idx_out, int B, long long n, int k,
+                      void* workspace, size_t workspace_bytes, gfb_stream_t stream);
+
+/* ---- K5: homography estimation + metric --------------------------------------------------------
+ * replaces estimation.py:60-92: convert_coordinates (:26-45), cv2.findHomography(RANSAC, thr 3,
+ * conf 0.99999) (:66-72), the diag(0,0,1) fallback (:73-77) and the 4-corner error (:79-92).
+ *   matches [B,N,4] normalised (xA,yA,xB,yB) in [-1,1]; weights [B,N] or NULL (= 1)
+ *   pixel coords: pa = ((wq-1)(xA+1)/2, (hq-1)(yA+1)/2), pb likewise with (wsup,hsup);
+ *   wq == 0 means `matches` already holds pixel coordinates (pos_a | pos_b), no conversion
+ *   n_hyp > 0: RANSAC over n_hyp hash-drawn 4-point models (threshold `thresh` px), then the
+ *              normalised DLT (OpenCV runKernel) on the best model's inliers and `gn_iters`
+ *              Gauss-Newton steps on the reprojection error (OpenCV's LM refinement).
+ *   n_hyp == 0: weighted DLT + refinement on all points (weights as given).
+ *   H_out [B,9] float64 row-major, h33 = 1; status[B] 1 = solved, 0 = fallback diag(0,0,1);
+ *   n_inliers[B]; mask_out [B,N] uint8 or NULL.  workspace >= gfb_homography_workspace_bytes. */
+size_t gfb_homography_workspace_bytes(int B, int N, int n_hyp);
+int gfb_homography_f32(const float* matches, const float* weights, int B, int N,
+                       float wq, float hq, float wsup, float hsup,
+                       int n_hyp, float thresh, int gn_iters, unsigned seed,
+                       double* H_out, int* status, int* n_inliers, unsigned char* mask_out,
+                       void* workspace, size_t workspace_bytes, gfb_stream_t stream);
+/* err[b] = min(clip, mean_k || proj(H_gt[b] c_k) - proj(H_pred[b] c_k) ||), c_k the 4 corners. */
+int gfb_corner_error_f64(const double* H_pred, const double* H_gt, float* err, int B,
+                         float w, float h, float clip, gfb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFNET_B200_H */
