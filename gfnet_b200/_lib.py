@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "_C", "libgfnet_b200.so")
 
 EXPORTS = [
     "gfb_abi_version", "gfb_strerror", "gfb_device_info", "gfb_local_corr_f32", "gfb_avg_pool2_f32",
+    "gfb_pad_rows_f32", "gfb_debug_local_corr_counters",
     "gfb_global_match_f32", "gfb_pos_embed_f32", "gfb_kde_f32", "gfb_match_postprocess_f32",
     "gfb_sample_keys_f32", "gfb_balance_keys_f32", "gfb_gather_matches_f32", "gfb_topk_workspace_bytes",
     "gfb_topk_desc_f32", "gfb_homography_workspace_bytes", "gfb_homography_f32", "gfb_corner_error_f64",
@@ -36,7 +37,9 @@ def _load():
     lib.gfb_strerror.restype = ctypes.c_char_p
     lib.gfb_strerror.argtypes = [i32]
     lib.gfb_device_info.argtypes = [ctypes.POINTER(i32)] * 3
-    lib.gfb_local_corr_f32.argtypes = [vp, vp, vp, vp] + [i32] * 13 + [vp]
+    lib.gfb_local_corr_f32.argtypes = [vp, vp, vp, vp] + [i32] * 14 + [vp]
+    lib.gfb_pad_rows_f32.argtypes = [vp, vp, i64, i32, i32, vp]
+    lib.gfb_debug_local_corr_counters.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), i32]
     lib.gfb_avg_pool2_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.gfb_global_match_f32.argtypes = [vp, vp, vp, vp] + [i32] * 8 + [vp]
     lib.gfb_pos_embed_f32.argtypes = [vp, vp] + [i32] * 5 + [vp]

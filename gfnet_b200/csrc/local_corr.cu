@@ -27,6 +27,7 @@ struct LcParams {
     const float* flow;
     float* out;
     int B, C, Hs, Ws, G, r;
+    int pitch;                 // floats between rows of f1 (>= Ws)
     int k_total, k_offset;
     int sample_mode, padding_mode;
     float ox0, ox1, oy0, oy1;  // torch.linspace endpoints of the window offsets (fp32)
@@ -58,13 +59,13 @@ __device__ float lc_generic_point(const LcParams& p, int b, int k, int gy, int g
         sy = fminf((float)(p.Hs - 1), fmaxf(sy, 0.f));
     }
     const float* f0 = p.f0 + (size_t)b * p.C * gg + (size_t)gy * p.G + gx;
-    const float* f1 = p.f1 + (size_t)b * p.C * p.Hs * p.Ws;
-    const size_t plane = (size_t)p.Hs * p.Ws;
+    const size_t plane = (size_t)p.Hs * p.pitch;
+    const float* f1 = p.f1 + (size_t)b * p.C * plane;
     float acc = 0.f;
     if (p.sample_mode == 1) {
         float rx = rintf(sx), ry = rintf(sy);
         if (rx >= 0.f && rx < (float)p.Ws && ry >= 0.f && ry < (float)p.Hs) {
-            size_t o = (size_t)(int)ry * p.Ws + (int)rx;
+            size_t o = (size_t)(int)ry * p.pitch + (int)rx;
             for (int c = 0; c < p.C; ++c) acc = fmaf(f0[c * gg], f1[c * plane + o], acc);
         }
         return acc * p.inv_sqrt_c;
@@ -82,8 +83,8 @@ __device__ float lc_generic_point(const LcParams& p, int b, int k, int gy, int g
     if (!yb) { w10 = 0.f; w11 = 0.f; }
     int xc0 = min(max(x0, 0), p.Ws - 1), xc1 = min(max(x0 + 1, 0), p.Ws - 1);
     int yc0 = min(max(y0, 0), p.Hs - 1), yc1 = min(max(y0 + 1, 0), p.Hs - 1);
-    size_t o00 = (size_t)yc0 * p.Ws + xc0, o01 = (size_t)yc0 * p.Ws + xc1;
-    size_t o10 = (size_t)yc1 * p.Ws + xc0, o11 = (size_t)yc1 * p.Ws + xc1;
+    size_t o00 = (size_t)yc0 * p.pitch + xc0, o01 = (size_t)yc0 * p.pitch + xc1;
+    size_t o10 = (size_t)yc1 * p.pitch + xc0, o11 = (size_t)yc1 * p.pitch + xc1;
     for (int c = 0; c < p.C; ++c) {
         const float* q = f1 + c * plane;
         float s = w00 * __ldg(q + o00) + w01 * __ldg(q + o01) + w10 * __ldg(q + o10) + w11 * __ldg(q + o11);
@@ -119,6 +120,10 @@ struct LcTile {
     int NCW;       // consumer warps
 };
 
+// debug counters: [0] tiles, [1] tiles without any streamed point, [2] points sent to the gather path,
+// [3] tiles whose box had to be centred (spread wider than BW)
+__device__ unsigned long long g_lc_stats[4];
+
 template <int CCH, int R, int P, int WP, bool F0REG>
 __global__ void __launch_bounds__(P >= 4 ? 224 : 352, 1)
 lc_stream_kernel(const LcParams p, const LcTile t, const __grid_constant__ CUtensorMap tmap_f1) {
@@ -131,7 +136,7 @@ lc_stream_kernel(const LcParams p, const LcTile t, const __grid_constant__ CUten
     const int stage_floats = CCH * t.BW;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)t.NST * stage_floats * sizeof(float));
     uint64_t* empty_bar = full_bar + t.NST;
-    __shared__ int s_red[6];  // xmin, xmax, ymin, ymax, overflow, live
+    __shared__ int s_red[8];  // xmin, xmax, sum(base), n threads | ymin, ymax, n fast points, n slow points
 
     const int G = p.G;
     const int tiles_x = (G + t.TC - 1) / t.TC, tiles_y = (G + t.TR - 1) / t.TR;
@@ -145,7 +150,8 @@ lc_stream_kernel(const LcParams p, const LcTile t, const __grid_constant__ CUten
     const size_t gg = (size_t)G * G;
 
     if (threadIdx.x == 0) {
-        s_red[0] = INT_MAX; s_red[1] = INT_MIN; s_red[2] = INT_MAX; s_red[3] = INT_MIN; s_red[4] = 0; s_red[5] = 0;
+        s_red[0] = INT_MAX; s_red[1] = INT_MIN; s_red[2] = 0; s_red[3] = 0;
+        s_red[4] = INT_MAX; s_red[5] = INT_MIN; s_red[6] = 0; s_red[7] = 0;
         for (int s = 0; s < t.NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], t.NCW); }
         mbar_fence_init();
     }
@@ -158,13 +164,13 @@ lc_stream_kernel(const LcParams p, const LcTile t, const __grid_constant__ CUten
     const int gx = tcx * t.TC + (has_pts ? tid % t.TC : 0);
     int yb[P], sh[P];
     float wx1[P], wy0[P], wy1[P];
-    bool valid[P], dead[P];
+    bool valid[P], fast[P], slow[P];
     int basex = INT_MAX;
 #pragma unroll
     for (int q = 0; q < P; ++q) {
         const int gy = tcy * t.TR + rg * P + q;
         valid[q] = has_pts && gy < G && gx < G;
-        dead[q] = true; yb[q] = 0; sh[q] = 0; wx1[q] = 0.f; wy0[q] = 0.f; wy1[q] = 0.f;
+        fast[q] = false; slow[q] = false; yb[q] = 0; sh[q] = 0; wx1[q] = 0.f; wy0[q] = 0.f; wy1[q] = 0.f;
         if (valid[q]) {
             const float* fl = p.flow + (size_t)b * 2 * gg + (size_t)gy * G + gx;
             float sx = unnormalize(__ldg(fl), p.Ws), sy = unnormalize(__ldg(fl + gg), p.Hs);
@@ -176,67 +182,83 @@ lc_stream_kernel(const LcParams p, const LcTile t, const __grid_constant__ CUten
                 wx1[q] = tx;
                 wy0[q] = (1.f - ty) * p.inv_sqrt_c;
                 wy1[q] = ty * p.inv_sqrt_c;
-                dead[q] = (xb >= p.Ws) || (xb + W <= 0) || (yb[q] >= p.Hs) || (yb[q] + W <= 0);
+                // a window entirely outside the image is all zeros (padding_mode "zeros"): neither fast nor slow
+                fast[q] = !((xb >= p.Ws) || (xb + W <= 0) || (yb[q] >= p.Hs) || (yb[q] + W <= 0));
                 sh[q] = xb;  // absolute for now
-                if (!dead[q]) basex = min(basex, xb);
+                if (fast[q]) basex = min(basex, xb);
             }
         }
     }
     bool any_live = basex != INT_MAX;
-    bool overflow = false;
-    int ymin = INT_MAX, ymax = INT_MIN;
     if (any_live) {
         basex &= ~3;  // floor to a 16-byte boundary (two's complement: works for negatives)
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            if (!dead[q]) {
+            if (fast[q]) {
                 sh[q] -= basex;
-                overflow |= sh[q] > SHMAX;
-                ymin = min(ymin, yb[q]);
-                ymax = max(ymax, yb[q] + W);
+                if (sh[q] > SHMAX) { fast[q] = false; slow[q] = true; }   // cannot share the thread's segment
             }
         }
     } else {
         basex = 0;
     }
     __syncthreads();  // s_red + barriers initialised
-    {
+    {   // phase 1: where to put the staged box in x
         int xmn = warp_min(any_live ? basex : INT_MAX), xmx = warp_max(any_live ? basex + WP : INT_MIN);
-        int ymn = warp_min(ymin), ymx = warp_max(ymax);
-        unsigned ov = __ballot_sync(0xffffffffu, overflow), lv = __ballot_sync(0xffffffffu, any_live);
-        if (lane == 0 && lv) {
+        int sm = any_live ? basex : 0, cn = any_live ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { sm += __shfl_xor_sync(0xffffffffu, sm, o); cn += __shfl_xor_sync(0xffffffffu, cn, o); }
+        if (lane == 0 && cn) {
             atomicMin(&s_red[0], xmn); atomicMax(&s_red[1], xmx);
-            atomicMin(&s_red[2], ymn); atomicMax(&s_red[3], ymx);
-            if (ov) atomicOr(&s_red[4], 1);
-            atomicOr(&s_red[5], 1);
+            atomicAdd(&s_red[2], sm); atomicAdd(&s_red[3], cn);
         }
     }
     __syncthreads();
-    const bool tile_live = s_red[5] != 0;
-    const int xbox0 = s_red[0] & ~3;
-    const int ylo = s_red[2], yhi = s_red[3];
-    const bool tile_overflow = tile_live && (s_red[4] != 0 || s_red[1] - xbox0 > t.BW);
-
-    float* outb = p.out + ((size_t)b * p.k_total + p.k_offset) * gg;
-
-    if (!tile_live || tile_overflow) {
-        // dead tile -> zeros; overflowing tile (window spread wider than the staged box or shear
-        // beyond the segment slack) -> exact per-sample gathers.
+    int xbox0 = 0;
+    bool centred = false;
+    if (s_red[3] > 0) {
+        xbox0 = s_red[0] & ~3;
+        if (s_red[1] - xbox0 > t.BW) {     // spread wider than the box: centre it on the mean segment
+            const int mean = s_red[2] / s_red[3];   // (sum of ~hundreds of |base| < 1e6 fits in int)
+            xbox0 = (mean + WP / 2 - t.BW / 2) & ~3;
+            centred = true;
+        }
+    }
+    if (any_live && (basex < xbox0 || basex + WP > xbox0 + t.BW)) {
+#pragma unroll
+        for (int q = 0; q < P; ++q) if (fast[q]) { fast[q] = false; slow[q] = true; }
+    }
+    {   // phase 2: rows to stream = union of the fast points' windows
+        int ymin = INT_MAX, ymax = INT_MIN, nf = 0, ns = 0;
 #pragma unroll
         for (int q = 0; q < P; ++q) {
-            if (!valid[q]) continue;
-            const int gy = tcy * t.TR + rg * P + q;
-            float* o = outb + (size_t)gy * G + gx;
-            for (int k = 0; k < KW * KW; ++k)
-                st_stream(o + (size_t)k * gg, tile_live ? lc_generic_point(p, b, k, gy, gx) : 0.f);
+            if (fast[q]) { ymin = min(ymin, yb[q]); ymax = max(ymax, yb[q] + W); ++nf; }
+            ns += slow[q];
         }
-        return;
+        ymin = warp_min(ymin); ymax = warp_max(ymax);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { nf += __shfl_xor_sync(0xffffffffu, nf, o); ns += __shfl_xor_sync(0xffffffffu, ns, o); }
+        if (lane == 0 && (nf | ns)) {
+            if (nf) { atomicMin(&s_red[4], ymin); atomicMax(&s_red[5], ymax); }
+            atomicAdd(&s_red[6], nf); atomicAdd(&s_red[7], ns);
+        }
+    }
+    __syncthreads();
+    const bool stream_any = s_red[6] > 0;
+    const int ylo = s_red[4], yhi = s_red[5];
+    if (threadIdx.x == 0) {
+        atomicAdd(&g_lc_stats[0], 1ull);
+        if (!stream_any) atomicAdd(&g_lc_stats[1], 1ull);
+        if (s_red[7]) atomicAdd(&g_lc_stats[2], (unsigned long long)s_red[7]);
+        if (centred) atomicAdd(&g_lc_stats[3], 1ull);
     }
 
+    float* outb = p.out + ((size_t)b * p.k_total + p.k_offset) * gg;
     const int nchunk = p.C / CCH;
+
     // ---- producer warp: stream rows [ylo, yhi) ∩ [0, Hs) x channel chunks through the ring -----
     if (!is_consumer) {
-        if (warp == t.NCW && lane == 0) {
+        if (stream_any && warp == t.NCW && lane == 0) {
             const uint32_t bytes = (uint32_t)stage_floats * sizeof(float);
             int seq = 0;
             for (int y = max(ylo, 0); y < min(yhi, p.Hs); ++y) {
@@ -252,43 +274,42 @@ lc_stream_kernel(const LcParams p, const LcTile t, const __grid_constant__ CUten
     }
 
     // ---- consumer threads ----------------------------------------------------------------------
-    float acc[P][WP], hprev[P][KW];
+    if (stream_any) {
+        float acc[P][WP], hprev[P][KW];
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
+        for (int q = 0; q < P; ++q) {
 #pragma unroll
-        for (int i = 0; i < WP; ++i) acc[q][i] = 0.f;
+            for (int i = 0; i < WP; ++i) acc[q][i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < KW; ++i) hprev[q][i] = 0.f;
-    }
-    const float* f0p[P];
-    float f0r[F0REG ? P : 1][F0REG ? CCH : 1];
-#pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const int gy = min(tcy * t.TR + rg * P + q, G - 1);
-        f0p[q] = p.f0 + (size_t)b * p.C * gg + (size_t)gy * G + min(gx, G - 1);
-        if (F0REG) {
-#pragma unroll
-            for (int c = 0; c < CCH; ++c) f0r[F0REG ? q : 0][F0REG ? c : 0] = (valid[q] && !dead[q]) ? __ldg(f0p[q] + (size_t)c * gg) : 0.f;
+            for (int i = 0; i < KW; ++i) hprev[q][i] = 0.f;
         }
-    }
-    const int xoff = basex - xbox0;  // multiple of 4 floats
-    int seq = 0;
-    for (int y = ylo; y < yhi; ++y) {
-        bool act[P];
-        bool any_act = false;
+        const float* f0p[P];
+        float f0r[F0REG ? P : 1][F0REG ? CCH : 1];
 #pragma unroll
-        for (int q = 0; q < P; ++q) { act[q] = !dead[q] && (unsigned)(y - yb[q]) < (unsigned)W; any_act |= act[q]; }
-        const bool warp_act = __any_sync(0xffffffffu, any_act);
-        if ((unsigned)y < (unsigned)p.Hs) {
-            for (int ch = 0; ch < nchunk; ++ch, ++seq) {
-                const int s = seq % t.NST;
-                // every consumer warp waits on every stage (even rows it skips): that bounds how far
-                // a warp can run ahead and keeps its empty-barrier arrivals in the right phase
-                mbar_wait(&full_bar[s], (seq / t.NST) & 1);
-                if (warp_act) {
+        for (int q = 0; q < P; ++q) {
+            const int gy = min(tcy * t.TR + rg * P + q, G - 1);
+            f0p[q] = p.f0 + (size_t)b * p.C * gg + (size_t)gy * G + min(gx, G - 1);
+            if (F0REG) {
+#pragma unroll
+                for (int c = 0; c < CCH; ++c) f0r[F0REG ? q : 0][F0REG ? c : 0] = fast[q] ? __ldg(f0p[q] + (size_t)c * gg) : 0.f;
+            }
+        }
+        const int xoff = max(basex - xbox0, 0);  // multiple of 4 floats (only used by fast points)
+        int seq = 0;
+        for (int y = ylo; y < yhi; ++y) {
+            bool act[P];
+            bool any_act = false;
+#pragma unroll
+            for (int q = 0; q < P; ++q) { act[q] = fast[q] && (unsigned)(y - yb[q]) < (unsigned)W; any_act |= act[q]; }
+            if ((unsigned)y < (unsigned)p.Hs) {
+                for (int ch = 0; ch < nchunk; ++ch, ++seq) {
+                    const int s = seq % t.NST;
+                    // every consumer warp waits on every stage (even rows it skips): that bounds how far
+                    // a warp can run ahead and keeps its empty-barrier arrivals in the right phase
+                    mbar_wait(&full_bar[s], (seq / t.NST) & 1);
                     if (any_act) {
                         const float* srow = ring + (size_t)s * stage_floats + xoff;
-#pragma unroll (F0REG ? CCH : 2)
+#pragma unroll (F0REG ? CCH : 4)
                         for (int c = 0; c < CCH; ++c) {
                             float seg[WP];
 #pragma unroll
@@ -307,50 +328,53 @@ lc_stream_kernel(const LcParams p, const LcTile t, const __grid_constant__ CUten
                             }
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
             }
-        }
-        // ---- finish D row j = y - yb for every active point: shift, lerp x, lerp y, store -----
+            // ---- finish D row j = y - yb for every active point: shift, lerp x, lerp y, store -----
 #pragma unroll
-        for (int q = 0; q < P; ++q) {
-            if (!act[q]) continue;
-            const int j = y - yb[q];
-            if (SHMAX >= 8 && (sh[q] & 8)) {
+            for (int q = 0; q < P; ++q) {
+                if (!act[q]) continue;
+                const int j = y - yb[q];
+                if (SHMAX >= 8 && (sh[q] & 8)) {
 #pragma unroll
-                for (int i = 0; i + 8 < WP; ++i) acc[q][i] = acc[q][i + 8];
+                    for (int i = 0; i + 8 < WP; ++i) acc[q][i] = acc[q][i + 8];
+                }
+                if (SHMAX >= 4 && (sh[q] & 4)) {
+#pragma unroll
+                    for (int i = 0; i + 4 < WP; ++i) acc[q][i] = acc[q][i + 4];
+                }
+                if (sh[q] & 2) {
+#pragma unroll
+                    for (int i = 0; i + 2 < WP; ++i) acc[q][i] = acc[q][i + 2];
+                }
+                if (sh[q] & 1) {
+#pragma unroll
+                    for (int i = 0; i + 1 < WP; ++i) acc[q][i] = acc[q][i + 1];
+                }
+                const float a1 = wx1[q], a0 = 1.f - a1;
+                float* o = outb + ((size_t)(j - 1) * KW) * gg + (size_t)(tcy * t.TR + rg * P + q) * G + gx;
+#pragma unroll
+                for (int i = 0; i < KW; ++i) {
+                    const float h = a0 * acc[q][i] + a1 * acc[q][i + 1];
+                    if (j >= 1) st_stream(o + (size_t)i * gg, wy0[q] * hprev[q][i] + wy1[q] * h);
+                    hprev[q][i] = h;
+                }
+#pragma unroll
+                for (int i = 0; i < WP; ++i) acc[q][i] = 0.f;
             }
-            if (SHMAX >= 4 && (sh[q] & 4)) {
-#pragma unroll
-                for (int i = 0; i + 4 < WP; ++i) acc[q][i] = acc[q][i + 4];
-            }
-            if (sh[q] & 2) {
-#pragma unroll
-                for (int i = 0; i + 2 < WP; ++i) acc[q][i] = acc[q][i + 2];
-            }
-            if (sh[q] & 1) {
-#pragma unroll
-                for (int i = 0; i + 1 < WP; ++i) acc[q][i] = acc[q][i + 1];
-            }
-            const float a1 = wx1[q], a0 = 1.f - a1;
-            float* o = outb + ((size_t)(j - 1) * KW) * gg + (size_t)(tcy * t.TR + rg * P + q) * G + gx;
-#pragma unroll
-            for (int i = 0; i < KW; ++i) {
-                const float h = a0 * acc[q][i] + a1 * acc[q][i + 1];
-                if (j >= 1) st_stream(o + (size_t)i * gg, wy0[q] * hprev[q][i] + wy1[q] * h);
-                hprev[q][i] = h;
-            }
-#pragma unroll
-            for (int i = 0; i < WP; ++i) acc[q][i] = 0.f;
         }
     }
-    // lattice points whose whole window lies outside the image: zeros (padding_mode "zeros")
+    // points that did not stream: window entirely outside the image -> zeros; segment outside the staged
+    // box (wild flow) -> exact per-sample gathers
 #pragma unroll
     for (int q = 0; q < P; ++q) {
-        if (valid[q] && dead[q]) {
-            float* o = outb + (size_t)(tcy * t.TR + rg * P + q) * G + gx;
-            for (int k = 0; k < KW * KW; ++k) st_stream(o + (size_t)k * gg, 0.f);
+        if (valid[q] && !fast[q]) {
+            const int gy = tcy * t.TR + rg * P + q;
+            float* o = outb + (size_t)gy * G + gx;
+            for (int k = 0; k < KW * KW; ++k)
+                st_stream(o + (size_t)k * gg, slow[q] ? lc_generic_point(p, b, k, gy, gx) : 0.f);
         }
     }
 }
@@ -366,35 +390,46 @@ __global__ void avg_pool2_kernel(const float* __restrict__ x, float* __restrict_
     }
 }
 
+__global__ void pad_rows_kernel(const float* __restrict__ x, float* __restrict__ y, size_t rows, int W, int pitch) {
+    const size_t total = rows * pitch;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int xx = (int)(t % pitch);
+        const size_t r = t / pitch;
+        y[t] = xx < W ? x[r * W + xx] : 0.f;
+    }
+}
+
 template <int CCH, int R, int P, int WP, bool F0REG>
 static int launch_stream(const LcParams& p, cudaStream_t st) {
-    constexpr int W = 2 * R + 2;
     LcTile t;
     const int G = p.G;
-    // tile columns: whole lattice rows up to 80 wide, else the largest divisor-friendly width
-    if (G <= 80) t.TC = G;
-    else if (G % 64 == 0) t.TC = 64;
-    else if (G % 80 == 0) t.TC = 80;
-    else if (G % 48 == 0) t.TC = 48;
-    else t.TC = 64;
+    const float s = (float)p.Ws / (float)G;
+    const int bw_full = ((p.Ws + 2 * WP + 3) / 4) * 4;
+    // tile columns: whole lattice rows up to 80 wide, else a divisor of G; shrink until the staged box
+    // (tile span x 1.6 slack for local magnification + segment + alignment) fits a 256-wide TMA box
+    const int cand[] = {80, 64, 48, 40, 32, 24, 16, 8};
+    t.TC = 0; t.BW = 0;
+    for (int ci = -1; ci < 8 && !t.TC; ++ci) {
+        const int tc = ci < 0 ? (G <= 80 ? G : 0) : cand[ci];
+        if (tc <= 0 || tc > G || (G % tc != 0 && !(ci == 7))) continue;
+        int bw = (((int)ceilf((float)tc * s * 1.6f) + WP + 8 + 3) / 4) * 4;
+        bw = min(bw, bw_full);
+        if (bw <= 256) { t.TC = tc; t.BW = bw; }
+    }
+    if (!t.TC) return GFB_EUNSUPPORTED;
     int NBR = max(1, min(8 / P, (P >= 4 ? 192 : 320) / t.TC));
     t.TR = NBR * P;
     t.NCW = (NBR * t.TC + 31) / 32;
-    const float s = (float)p.Ws / (float)G;
-    int bw_tile = (int)ceilf((float)t.TC * s * 1.35f) + WP + 8;
-    int bw_full = p.Ws + 2 * WP;
-    t.BW = ((min(bw_tile, bw_full) + 3) / 4) * 4;
-    if (t.BW > 256) return GFB_EUNSUPPORTED;
     const size_t stage_bytes = (size_t)CCH * t.BW * sizeof(float);
     t.NST = (int)min((size_t)6, (size_t)(200 * 1024) / stage_bytes);
     if (t.NST < 2) return GFB_EUNSUPPORTED;
     // keep two CTAs per SM resident when the ring allows it
-    if (t.NST > 4 && (size_t)t.NST * stage_bytes > 100 * 1024) t.NST = (int)max((size_t)3, (size_t)(100 * 1024) / stage_bytes);
+    if ((size_t)t.NST * stage_bytes > 100 * 1024) t.NST = (int)max((size_t)3, (size_t)(100 * 1024) / stage_bytes);
     const size_t smem = (size_t)t.NST * stage_bytes + 2 * t.NST * sizeof(uint64_t);
 
     CUtensorMap tmap;
     uint64_t dims[3] = {(uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B * p.C};
-    uint64_t strides[2] = {(uint64_t)p.Ws * 4, (uint64_t)p.Hs * p.Ws * 4};
+    uint64_t strides[2] = {(uint64_t)p.pitch * 4, (uint64_t)p.Hs * p.pitch * 4};
     uint32_t box[3] = {(uint32_t)t.BW, 1u, (uint32_t)CCH};
     int rc = gfb_encode_tmap_f32(&tmap, p.f1, 3, dims, strides, box, 0);
     if (rc != GFB_OK) return rc;
@@ -404,8 +439,23 @@ static int launch_stream(const LcParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     const int tiles = p.B * ((G + t.TR - 1) / t.TR) * ((G + t.TC - 1) / t.TC);
     kern<<<tiles, (t.NCW + 1) * 32, smem, st>>>(p, t, tmap);
-    (void)W;
     GFB_LAUNCH_RESULT();
+}
+
+// one point per thread, minimal segment: the default (robust to per-point flow jitter)
+template <int CCH, bool F0REG>
+static int launch_stream_p1(const LcParams& p, cudaStream_t st) {
+    switch (p.r) {
+        case 1: return launch_stream<CCH, 1, 1, 8, F0REG>(p, st);
+        case 2: return launch_stream<CCH, 2, 1, 12, F0REG>(p, st);
+        case 3: return launch_stream<CCH, 3, 1, 12, F0REG>(p, st);
+        case 4: return launch_stream<CCH, 4, 1, 16, F0REG>(p, st);
+        case 5: return launch_stream<CCH, 5, 1, 16, F0REG>(p, st);
+        case 6: return launch_stream<CCH, 6, 1, 20, F0REG>(p, st);
+        case 7: return launch_stream<CCH, 7, 1, 20, F0REG>(p, st);
+        case 8: return launch_stream<CCH, 8, 1, 24, F0REG>(p, st);
+        default: return GFB_EUNSUPPORTED;
+    }
 }
 
 }  // namespace gfb
@@ -420,12 +470,31 @@ extern "C" int gfb_avg_pool2_f32(const float* x, float* y, int N, int H, int W, 
     GFB_LAUNCH_RESULT();
 }
 
+extern "C" int gfb_pad_rows_f32(const float* x, float* y, long long rows, int W, int pitch, gfb_stream_t stream) {
+    GFB_CHECK_ARG(x && y && rows > 0 && W > 0 && pitch >= W);
+    size_t total = (size_t)rows * pitch;
+    int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+    pad_rows_kernel<<<blocks, 256, 0, gfb_cu(stream)>>>(x, y, (size_t)rows, W, pitch);
+    GFB_LAUNCH_RESULT();
+}
+
+extern "C" int gfb_debug_local_corr_counters(unsigned long long* host_out4, int reset) {
+    cudaError_t e = cudaSuccess;
+    if (host_out4) e = cudaMemcpyFromSymbol(host_out4, g_lc_stats, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(g_lc_stats, z, sizeof(z));
+    }
+    return e == cudaSuccess ? GFB_OK : (int)e;
+}
+
 extern "C" int gfb_local_corr_f32(const float* f0, const float* f1, const float* flow, float* out,
-                                  int B, int C, int Hs, int Ws, int G, int r,
+                                  int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                                   int win_h, int win_w, int sample_mode, int padding_mode,
                                   int k_total, int k_offset, int algo, gfb_stream_t stream) {
     GFB_CHECK_ARG(f0 && f1 && flow && out);
     GFB_CHECK_ARG(B > 0 && C > 0 && Hs > 0 && Ws > 0 && G > 0 && r >= 0 && win_h > 0 && win_w > 0);
+    GFB_CHECK_ARG(f1_pitch == 0 || f1_pitch >= Ws);
     GFB_CHECK_ARG(sample_mode == 0 || sample_mode == 1);
     GFB_CHECK_ARG(padding_mode == 0 || padding_mode == 1);
     const int kk = (2 * r + 1) * (2 * r + 1);
@@ -434,6 +503,7 @@ extern "C" int gfb_local_corr_f32(const float* f0, const float* f1, const float*
     LcParams p;
     p.f0 = f0; p.f1 = f1; p.flow = flow; p.out = out;
     p.B = B; p.C = C; p.Hs = Hs; p.Ws = Ws; p.G = G; p.r = r;
+    p.pitch = f1_pitch ? f1_pitch : Ws;
     p.k_total = k_total; p.k_offset = k_offset;
     p.sample_mode = sample_mode; p.padding_mode = padding_mode;
     // python: torch.linspace(-2*r/n, 2*r/n, 2r+1): endpoints are doubles rounded to fp32
@@ -443,55 +513,28 @@ extern "C" int gfb_local_corr_f32(const float* f0, const float* f1, const float*
     cudaStream_t st = gfb_cu(stream);
 
     const bool stream_ok = win_h == Hs && win_w == Ws && sample_mode == 0 && padding_mode == 0 &&
-                           r >= 1 && r <= 8 && (Ws % 4 == 0) && gfb_aligned(f1, 16) &&
+                           r >= 1 && r <= 8 && (p.pitch % 4 == 0) && gfb_aligned(f1, 16) &&
                            (C % 16 == 0) && (size_t)B * C < (1ull << 31);
     if (algo == 2 && !stream_ok) return GFB_EUNSUPPORTED;
     if (algo != 1 && stream_ok) {
-        const int variant = algo >> 4;  // tuning knob: 0 = default table
+        const int variant = algo >> 4;  // tuning knob: 0/1 = one point per thread, 2 / 4 = P points share a segment
         int rc = GFB_EUNSUPPORTED;
-#define LC_CASE(CCH_, R_, P_, WP_, F0_) rc = launch_stream<CCH_, R_, P_, WP_, F0_>(p, st)
-        if (variant == 0 || variant == 2) {
-            if (C == 16) {
-                switch (r) {
-                    case 1: LC_CASE(16, 1, 2, 8, true); break;
-                    case 2: LC_CASE(16, 2, 2, 12, true); break;
-                    case 3: LC_CASE(16, 3, 2, 12, true); break;
-                    case 4: LC_CASE(16, 4, 2, 16, true); break;
-                    default: break;
-                }
-            } else if (C == 32) {
-                switch (r) {
-                    case 2: LC_CASE(32, 2, 2, 12, true); break;
-                    case 3: LC_CASE(32, 3, 2, 12, true); break;
-                    case 4: LC_CASE(32, 4, 2, 16, true); break;
-                    case 6: LC_CASE(32, 6, 2, 20, false); break;
-                    default: break;
-                }
-            } else if (C % 64 == 0) {
-                switch (r) {
-                    case 2: LC_CASE(64, 2, 2, 12, false); break;
-                    case 3: LC_CASE(64, 3, 2, 12, false); break;
-                    case 4: LC_CASE(64, 4, 2, 16, false); break;
-                    case 5: LC_CASE(64, 5, 2, 16, false); break;
-                    case 6: LC_CASE(64, 6, 2, 20, false); break;
-                    case 7: LC_CASE(64, 7, 2, 20, false); break;
-                    case 8: LC_CASE(64, 8, 2, 24, false); break;
-                    default: break;
-                }
-            }
-        } else if (variant == 1) {  // one point per thread
-            if (C == 16 && r == 2) LC_CASE(16, 2, 1, 12, true);
-            else if (C == 32 && r == 4) LC_CASE(32, 4, 1, 16, true);
-            else if (C % 64 == 0 && r == 6) LC_CASE(64, 6, 1, 20, false);
-            else if (C % 64 == 0 && r == 7) LC_CASE(64, 7, 1, 20, false);
-        } else if (variant == 4) {  // four points per thread
-            if (C == 16 && r == 2) LC_CASE(16, 2, 4, 12, true);
-            else if (C == 32 && r == 4) LC_CASE(32, 4, 4, 16, false);
-            else if (C % 64 == 0 && r == 6) LC_CASE(64, 6, 4, 20, false);
-            else if (C % 64 == 0 && r == 7) LC_CASE(64, 7, 4, 24, false);
+        if (variant <= 1) {
+            if (C == 16) rc = launch_stream_p1<16, true>(p, st);
+            else if (C == 32) rc = launch_stream_p1<32, true>(p, st);
+            else if (C % 64 == 0) rc = launch_stream_p1<64, false>(p, st);
+        } else if (variant == 2) {
+            if (C == 16 && r == 2) rc = launch_stream<16, 2, 2, 12, true>(p, st);
+            else if (C == 32 && r == 4) rc = launch_stream<32, 4, 2, 16, true>(p, st);
+            else if (C % 64 == 0 && r == 6) rc = launch_stream<64, 6, 2, 20, false>(p, st);
+            else if (C % 64 == 0 && r == 7) rc = launch_stream<64, 7, 2, 20, false>(p, st);
+        } else if (variant == 4) {
+            if (C == 16 && r == 2) rc = launch_stream<16, 2, 4, 12, true>(p, st);
+            else if (C == 32 && r == 4) rc = launch_stream<32, 4, 4, 16, false>(p, st);
+            else if (C % 64 == 0 && r == 6) rc = launch_stream<64, 6, 4, 20, false>(p, st);
+            else if (C % 64 == 0 && r == 7) rc = launch_stream<64, 7, 4, 24, false>(p, st);
         }
-#undef LC_CASE
-        if (rc != GFB_EUNSUPPORTED || algo == 2 || (algo >> 4) != 0) return rc;
+        if (rc != GFB_EUNSUPPORTED || algo == 2 || variant != 0) return rc;
     }
     if (algo >= 2) return GFB_EUNSUPPORTED;
     const size_t total = (size_t)B * kk * G * G;

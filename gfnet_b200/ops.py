@@ -63,7 +63,13 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
     with torch.cuda.device(f0.device):
         for level in range(num_level):
             hs, ws = int(f1.shape[2]), int(f1.shape[3])
-            rc = lib.gfb_local_corr_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, G, r, win_h, win_w,
+            src, pitch = f1, 0
+            if ws % 4 and algo != ALGO_GENERIC and _stream_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
+                # TMA needs 16-byte global strides: pad each row once (e.g. ws = 70 -> pitch 72)
+                pitch = (ws + 3) // 4 * 4
+                src = torch.empty((B, c, hs, pitch), device=f1.device, dtype=f1.dtype)
+                check(lib.gfb_pad_rows_f32(ptr(f1), ptr(src), B * c * hs, ws, pitch, st), "pad_rows")
+            rc = lib.gfb_local_corr_f32(ptr(f0), ptr(src), ptr(fl), ptr(out), B, c, hs, ws, pitch, G, r, win_h, win_w,
                                         _SAMPLE_MODES[sample_mode], _PADDING_MODES[padding_mode],
                                         kk * num_level, kk * level, int(algo), st)
             check(rc, "local_correlation")
@@ -72,6 +78,19 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
                 check(lib.gfb_avg_pool2_f32(ptr(f1), ptr(nxt), B * c, hs, ws, st), "avg_pool2")
                 f1 = nxt
     return out
+
+
+def _stream_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
+    return (win_h == hs and win_w == ws and sample_mode == "bilinear" and padding_mode == "zeros"
+            and 1 <= r <= 8 and c % 16 == 0 and (c in (16, 32) or c % 64 == 0))
+
+
+def local_correlation_counters(reset=True):
+    """(tiles, tiles without streamed points, points on the gather path, centred tiles); synchronises."""
+    import ctypes
+    buf = (ctypes.c_ulonglong * 4)()
+    check(lib.gfb_debug_local_corr_counters(buf, int(reset)), "counters")
+    return tuple(int(v) for v in buf)
 
 
 def kde(x, std=0.1, half=True, down=None):

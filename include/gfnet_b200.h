@@ -53,14 +53,22 @@ int gfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *        grid_based_correlation=True (local_correlation.py:33-52).
  *   sample_mode 0 = bilinear, 1 = nearest; padding_mode 0 = zeros, 1 = border; align_corners=False.
  *   algo 0 = auto, 1 = generic gather kernel, 2 = TMA row-streaming kernel (requires
- *        win == (Ws,Hs), bilinear, zeros, C in {8,16,32,64}, 1 <= r <= 8, Ws % 4 == 0).
+ *        win == (Ws,Hs), bilinear, zeros, C in {16, 32, 64k}, 1 <= r <= 8, pitch % 4 == 0).
+ *   f1_pitch: floats between consecutive rows of f1 (0 = Ws).  The TMA kernel needs a pitch that is a
+ *        multiple of 4 (16-byte global strides); callers with Ws % 4 != 0 (e.g. 70) pad rows once with
+ *        gfb_pad_rows_f32 and pass the padded pitch.
  * num_level > 1 (local_correlation.py:61-71) = one call per level with `gfb_avg_pool2_f32` between. */
 int gfb_local_corr_f32(const float* f0, const float* f1, const float* flow, float* out,
-                       int B, int C, int Hs, int Ws, int G, int r,
+                       int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                        int win_h, int win_w, int sample_mode, int padding_mode,
                        int k_total, int k_offset, int algo, gfb_stream_t stream);
 /* F.avg_pool2d(x, 2, 2) on [N,H,W] planes -> [N,H/2,W/2] (local_correlation.py:71). */
 int gfb_avg_pool2_f32(const float* x, float* y, int N, int H, int W, gfb_stream_t stream);
+/* y[rows, pitch] = x[rows, W] with zero fill of the tail of each row. */
+int gfb_pad_rows_f32(const float* x, float* y, long long rows, int W, int pitch, gfb_stream_t stream);
+/* Debug/profiling aid (synchronises!): tiles launched, tiles without streamed points, lattice points
+ * that took the gather path, tiles whose staged box was centred; host_out4 may be NULL; reset != 0 zeroes. */
+int gfb_debug_local_corr_counters(unsigned long long* host_out4, int reset);
 
 /* ---- K2: coarse global match --------------------------------------------------------------
  * replaces GFNet.corr_volume + GFNet.pos_embed, model/network.py:415-440 (call site :251-252).

@@ -19,7 +19,10 @@ def gf():
     return gfnet_b200
 
 
-def _close(a, b, rtol=1e-4, atol_rel=1e-5):
+def _close(a, b, rtol=1e-4, atol_rel=4e-5):
+    # local_correlation: the reference's own per-sample fp32 coordinate arithmetic ((x+1)*W-1)/2 carries
+    # ~1 ulp(W) ~ 1.5e-5 px of noise at W = 224..280; times the feature gradient that is a few 1e-5 of
+    # max|corr| in absolute terms, hence atol = 4e-5 * max|ref| next to rtol = 1e-4.
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
     atol = atol_rel * float(b.abs().max()) + 1e-12
     bad = (a - b).abs() > atol + rtol * b.abs()
@@ -85,9 +88,13 @@ def test_local_correlation_stream_kernel_is_used(gf):
         out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=2)
         ref = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=1)
         _close(out, ref)
-    with pytest.raises(NotImplementedError):
-        f0, f1, flow = synth.scale_inputs([synth.random_homography(cgen)], 64, 70, 40, gen, "cuda")
-        gf.local_correlation((1, 64, 70, 70), f0, f1, 6, 40, flow=flow, algo=2)
+    # ws = 70: rows are padded to a 16-byte pitch so the TMA kernel still applies
+    f0, f1, flow = synth.scale_inputs([synth.random_homography(cgen)], 64, 70, 40, gen, "cuda")
+    _close(gf.local_correlation((1, 64, 70, 70), f0, f1, 6, 40, flow=flow, algo=2),
+           gf.local_correlation((1, 64, 70, 70), f0, f1, 6, 40, flow=flow, algo=1))
+    with pytest.raises(NotImplementedError):   # 24 channels: not a streaming-kernel configuration
+        f0, f1, flow = synth.scale_inputs([synth.random_homography(cgen)], 24, 32, 32, gen, "cuda")
+        gf.local_correlation((1, 24, 32, 32), f0, f1, 6, 32, flow=flow, algo=2)
 
 
 def test_local_correlation_edge_flows(gf):
@@ -101,7 +108,7 @@ def test_local_correlation_edge_flows(gf):
     for shift in (0.0, 2.5, -3.0, 0.999):
         flow = torch.stack((xx + shift, yy - shift), 0)[None].contiguous()
         ref = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
-        for algo in (0, 1, 2 | (1 << 4), 2 | (4 << 4)):
+        for algo in (0, 1, 2, 2 | (2 << 4), 2 | (4 << 4)):
             _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=algo), ref)
 
 

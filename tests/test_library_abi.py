@@ -33,7 +33,7 @@ def test_error_strings_and_host_side_validation():
     assert b"invalid" in lib.gfb_strerror(-1) and b"not supported" in lib.gfb_strerror(-2)
     null = ctypes.c_void_p(0)
     assert lib.gfb_kde_f32(null, null, 1, 10, 4, 1, 0.1, null) == _lib.GFB_EINVAL
-    assert lib.gfb_local_corr_f32(null, null, null, null, *([1] * 13), null) == _lib.GFB_EINVAL
+    assert lib.gfb_local_corr_f32(null, null, null, null, *([1] * 14), null) == _lib.GFB_EINVAL
     assert lib.gfb_topk_workspace_bytes(2, 1000, 100) == 2 * 2 * 5120 * 4
     assert lib.gfb_topk_workspace_bytes(1, 204800, 20000) == 2 * 20480 * 4
     assert lib.gfb_homography_workspace_bytes(3, 5000, 512) >= 3 * 8 + 3 * 512 * 72

@@ -41,7 +41,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--b", type=int, default=64)
     ap.add_argument("--out", default="gpurun_out/kbench.json")
-    ap.add_argument("--variants", default="0,18,66")
+    ap.add_argument("--variants", default="0,34,66")
     args = ap.parse_args()
     dev = "cuda"
     gen = torch.Generator(device=dev).manual_seed(0)
@@ -61,7 +61,11 @@ def main():
                                    iters=5 if algo == 1 else 10, flush=flush)
             except NotImplementedError:
                 continue
-            row = dict(scale=s, c=c, hs=hs, G=g, r=r, algo=algo, ms=med, ms_best=best, GBps=nbytes / med / 1e6,
+            from gfnet_b200.ops import local_correlation_counters
+            local_correlation_counters(reset=True)
+            gf.local_correlation((b, c, hs, hs), f0, f1, r, g, flow=flow, algo=algo, out=out)
+            cnt = local_correlation_counters(reset=True)
+            row = dict(scale=s, c=c, hs=hs, G=g, r=r, algo=algo, ms=med, ms_best=best, GBps=nbytes / med / 1e6, counters=cnt,
                        frac=nbytes / med / 1e6 / PEAK_HBM, fma_T=(b * c * (2 * r + 2) ** 2 * g * g) / med / 1e9)
             res["local_corr"].append(row)
             print(json.dumps(row), flush=True)
