@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py -- image pairs/s of the GFNet hot path (coarse match + local correlation at every scale /
+iteration / pass + post-process + balanced sampling with kde + homography + corner error).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    the reference's CPU path (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[1]): vis_ir.json, 448x448 pairs (+ the 560 upsample pass the reference
+always runs), num_itr = 2, 32 pairs per GPU (op batch 64, symmetric), synthetic pyramids / random H.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "image pairs/s at 448^2 (corr+kde+H)"
+UNIT = "pairs/s"
+PAIRS_PER_GPU = 32
+NUM_ITR = 2
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def config_dict(n_gpus, extra=None):
+    cfg = {"workload": "vis_ir.json 448x448 pairs (pass 1 at 448 + upsample pass at 560), num_itr=2, symmetric",
+           "pairs_per_gpu": PAIRS_PER_GPU, "global_pairs": PAIRS_PER_GPU * n_gpus, "num_samples": 5000,
+           "kde_points": 20000, "ransac_hypotheses": 512, "parallelism": f"pairs sharded over {n_gpus} GPU(s), one all_gather of [B,12]",
+           "l2": "inputs 1.3 GB + outputs 0.66 GB per step >> 126 MB L2 (no flush needed)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port of its own torch/cv2 calls) on host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from gfnet_b200 import synth            # data generation only (CPU tensors)
+    from oracle.pipeline import cpu_hot_path
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_pairs = 1
+    batches = [synth.PairBatch(sample_pairs, num_itr=NUM_ITR, seed=1234, device="cpu", pair_offset=i) for i in range(2)]
+    for w in range(args.warmup):
+        cpu_hot_path(batches[w % 2])
+    timings = {}
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_hot_path(batches[s % 2], timings=timings)
+    dt = time.perf_counter() - t0
+    value = sample_pairs * args.steps / dt
+    base = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_pairs} pair per step (op batch 2) of the same workload, torch {torch.__version__} CPU with {cores} threads, "
+                      f"kde(half=False, down=8) as the reference does on CPU, cv2.findHomography RANSAC",
+            "seconds_by_stage_per_pair": {k: v / (sample_pairs * args.steps) for k, v in timings.items()}}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": config_dict(args.gpus, {"reference_sample_pairs_per_step": sample_pairs}),
+                      "cpu_baseline": base,
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gfnet_b200 as gf
+    from gfnet_b200 import synth
+    from gfnet_b200.pipeline import HotPath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    B = PAIRS_PER_GPU
+    batch = synth.PairBatch(B, num_itr=NUM_ITR, seed=1234, device=dev, rank=rank)
+    hp = HotPath()
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    gathered = [torch.empty((B, 12), device=dev, dtype=torch.float64) for _ in range(world)] if world > 1 else None
+
+    def step(b=batch):
+        out = hp.run(b, generator=gen)
+        if world > 1:
+            dist.all_gather(gathered, out["result"])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    hp.timing = []                     # CUDA-event pairs around every local_correlation launch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    lc_ms = sum(a.elapsed_time(b) for (_, a, b) in hp.timing)
+    lc_by_scale = {}
+    for (key, a, b_) in hp.timing:
+        lc_by_scale[key] = lc_by_scale.get(key, 0.0) + a.elapsed_time(b_)
+    n_lc = len(hp.timing)
+    hp.timing = None
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = B * world * args.steps / (total_ms / 1e3)
+
+    # ---- end to end: host (pinned) inputs -> device -> path -> host result, every step
+    tensors = batch.tensors()
+    pinned = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in tensors]
+    h2d = sum(t.numel() * t.element_size() for t in tensors)
+    res_host = torch.empty((B, 12), dtype=torch.float64, pin_memory=True)
+    d2h = res_host.numel() * res_host.element_size()
+
+    def e2e_step():
+        for dst, src in zip(tensors, pinned):
+            dst.copy_(src, non_blocking=True)
+        o = step()
+        res_host.copy_(o["result"], non_blocking=True)
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ems = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * e2e_steps / (float(ems.item()) / 1e3)
+
+    if rank == 0:
+        peaks, src = measured_peaks()
+        lc_bytes = 0
+        by_scale = {}
+        for pi, scales in enumerate(batch.passes):
+            for sc in scales:
+                nb = gf.local_correlation_bytes(2 * B, sc["c"], sc["hs"], sc["hs"], sc["G"], sc["r"]) * len(sc["flows"])
+                lc_bytes += nb
+                k = f"pass{pi + 1}_scale{sc['scale']}"
+                t_ms = lc_by_scale.get(k, 0.0) / args.steps
+                by_scale[k] = {"GBps": nb / t_ms / 1e6 if t_ms else None, "frac": nb / t_ms / 1e6 / peaks["hbm_gbs"] if t_ms else None,
+                               "ms_per_step": t_ms}
+        achieved = lc_bytes * args.steps / (lc_ms / 1e3) / 1e9 if lc_ms else None
+        roofline = {"kernel": "lc_stream_kernel (local_correlation, all scales/iterations/passes of a step)", "bound": "hbm",
+                    "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": src, "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"] if achieved else None, "traffic": None,
+                    "algorithmic_bytes_per_step": lc_bytes, "launches_per_step": n_lc // max(args.steps, 1),
+                    "share_of_step": lc_ms / total_ms if total_ms else None, "by_scale": by_scale}
+        # CPU baseline on this box's host cores: bounded sample (1 pair x 2 steps)
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle.pipeline import cpu_hot_path
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cb = synth.PairBatch(1, num_itr=NUM_ITR, seed=1234, device="cpu")
+            cpu_hot_path(cb)
+            t0 = time.perf_counter()
+            tm = {}
+            nrep = 2
+            for _ in range(nrep):
+                cpu_hot_path(cb, timings=tm)
+            dt = time.perf_counter() - t0
+            cpu = {"value": nrep / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"1 pair per step x {nrep} steps of the same workload (oracle port of the reference's torch/cv2 calls, {cores} threads)",
+                   "seconds_by_stage_per_pair": {k: v / nrep for k, v in tm.items()}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config_dict(world),
+                "clocks": clocks, "gpu_launches": hp.kernel_launches(batch) * args.steps,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "ace_px_mean": float(out["err"].mean()), "solved": int(out["status"].sum())}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 3 if args.steps is None else min(args.steps, 6)     # ~6 s of CPU work per pair
+        args.warmup = 1 if args.warmup is None else min(args.warmup, 2)
+        run_reference(args)
+    else:
+        args.steps = 20 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else args.warmup
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

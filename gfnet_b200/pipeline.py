@@ -15,6 +15,7 @@ class HotPath:
     def __init__(self, num_samples=5000, n_hyp=512, precision=0, lc_algo=0, seed=0):
         self.num_samples, self.n_hyp, self.precision, self.lc_algo, self.seed = num_samples, n_hyp, precision, lc_algo, seed
         self._corr = {}
+        self.timing = None    # list of (key, start_event, end_event) when bench.py wants per-launch device times
 
     def _corr_buf(self, key, shape, device):
         buf = self._corr.get(key)
@@ -39,7 +40,13 @@ class HotPath:
                 b, c, hs, G, r = sc["f1"].shape[0], sc["c"], sc["hs"], sc["G"], sc["r"]
                 for it, flow in enumerate(sc["flows"]):
                     buf = self._corr_buf((pi, sc["scale"]), (b, (2 * r + 1) ** 2, G, G), flow.device)
+                    if self.timing is not None:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
                     ops.local_correlation((b, c, hs, hs), sc["f0"], sc["f1"], r, G, flow=flow, algo=self.lc_algo, out=buf)
+                    if self.timing is not None:
+                        e1.record()
+                        self.timing.append((f"pass{pi + 1}_scale{sc['scale']}", e0, e1))
         out["last_corr"] = buf
         warp, cert = matcher.match_postprocess(batch.final_flow, batch.cert_logits, symmetric=True)
         m, c = matcher.sample_batched(warp, cert, self.num_samples, generator=generator, noise=noise)
