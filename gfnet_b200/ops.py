@@ -19,6 +19,10 @@ _SAMPLE_MODES = {"bilinear": 0, "nearest": 1}
 _PADDING_MODES = {"zeros": 0, "border": 1}
 
 ALGO_AUTO, ALGO_GENERIC, ALGO_STREAM = 0, 1, 2
+# tuning variants (algo = base | variant << 4 | column-divisor override << 8 | quad-row override << 12)
+ALGO_STREAM_P1 = 2 | (1 << 4)       # one lattice point per thread
+ALGO_QUAD_LDS128 = 2 | (8 << 4)     # 4 points per lane, FFMA2, 16-byte aligned segments
+ALGO_QUAD_LDS64 = 2 | (9 << 4)      # same, 8-byte aligned segments (default)
 
 
 def local_correlation(featuremap_size, feature0, feature1, local_radius, num_grid,
@@ -64,7 +68,7 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
         for level in range(num_level):
             hs, ws = int(f1.shape[2]), int(f1.shape[3])
             src, pitch = f1, 0
-            if ws % 4 and algo != ALGO_GENERIC and _stream_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
+            if ws % 4 and (int(algo) & 15) != ALGO_GENERIC and _stream_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
                 # TMA needs 16-byte global strides: pad each row once (e.g. ws = 70 -> pitch 72)
                 pitch = (ws + 3) // 4 * 4
                 src = torch.empty((B, c, hs, pitch), device=f1.device, dtype=f1.dtype)
@@ -88,7 +92,7 @@ def _stream_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
 def local_correlation_counters(reset=True):
     """(tiles, tiles without streamed points, points on the gather path, centred tiles); synchronises."""
     import ctypes
-    buf = (ctypes.c_ulonglong * 4)()
+    buf = (ctypes.c_ulonglong * 8)()
     check(lib.gfb_debug_local_corr_counters(buf, int(reset)), "counters")
     return tuple(int(v) for v in buf)
 

@@ -66,9 +66,10 @@ int gfb_local_corr_f32(const float* f0, const float* f1, const float* flow, floa
 int gfb_avg_pool2_f32(const float* x, float* y, int N, int H, int W, gfb_stream_t stream);
 /* y[rows, pitch] = x[rows, W] with zero fill of the tail of each row. */
 int gfb_pad_rows_f32(const float* x, float* y, long long rows, int W, int pitch, gfb_stream_t stream);
-/* Debug/profiling aid (synchronises!): tiles launched, tiles without streamed points, lattice points
- * that took the gather path, tiles whose staged box was centred; host_out4 may be NULL; reset != 0 zeroes. */
-int gfb_debug_local_corr_counters(unsigned long long* host_out4, int reset);
+/* Debug/profiling aid (synchronises!): host_out8[0..3] = tiles launched, tiles without streamed points, lattice
+ * points that took the gather path, tiles whose staged box was centred; [4..7] = SM clocks summed over CTAs
+ * (set-up, wait for the first row, row loop, tail).  host_out8 may be NULL; reset != 0 zeroes. */
+int gfb_debug_local_corr_counters(unsigned long long* host_out8, int reset);
 
 /* ---- K2: coarse global match --------------------------------------------------------------
  * replaces GFNet.corr_volume + GFNet.pos_embed, model/network.py:415-440 (call site :251-252).

@@ -75,6 +75,13 @@ def test_local_correlation_shapes(gf, shape, kind):
     _close(out, ref)
     gen_out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=1)
     _close(gen_out, ref)
+    for variant in (1, 8, 9):      # P = 1 stream kernel, quad kernel with LDS.128 / LDS.64 segments
+        try:
+            v_out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=2 | (variant << 4))
+        except NotImplementedError:
+            assert variant != 1
+            continue
+        _close(v_out, ref)
 
 
 def test_local_correlation_stream_kernel_is_used(gf):
@@ -108,7 +115,7 @@ def test_local_correlation_edge_flows(gf):
     for shift in (0.0, 2.5, -3.0, 0.999):
         flow = torch.stack((xx + shift, yy - shift), 0)[None].contiguous()
         ref = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
-        for algo in (0, 1, 2, 2 | (2 << 4), 2 | (4 << 4)):
+        for algo in (0, 1, 2, 2 | (1 << 4), 2 | (2 << 4), 2 | (4 << 4), 2 | (8 << 4), 2 | (9 << 4)):
             _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=algo), ref)
 
 

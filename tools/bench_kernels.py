@@ -41,7 +41,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--b", type=int, default=64)
     ap.add_argument("--out", default="gpurun_out/kbench.json")
-    ap.add_argument("--variants", default="0,34,66")
+    ap.add_argument("--variants", default="18,130,146")
+    ap.add_argument("--lc-only", action="store_true")
+    ap.add_argument("--no-generic", action="store_true")
     args = ap.parse_args()
     dev = "cuda"
     gen = torch.Generator(device=dev).manual_seed(0)
@@ -55,7 +57,7 @@ def main():
         f0, f1, flow = synth.scale_inputs(Hs, c, hs, g, gen, dev)
         out = torch.empty((b, (2 * r + 1) ** 2, g, g), device=dev)
         nbytes = gf.local_correlation_bytes(b, c, hs, hs, g, r)
-        for algo in [int(v) for v in args.variants.split(",")] + [1]:
+        for algo in [int(v) for v in args.variants.split(",")] + ([] if args.no_generic else [1]):
             try:
                 med, best = timeit(lambda: gf.local_correlation((b, c, hs, hs), f0, f1, r, g, flow=flow, algo=algo, out=out),
                                    iters=5 if algo == 1 else 10, flush=flush)
@@ -70,6 +72,9 @@ def main():
             res["local_corr"].append(row)
             print(json.dumps(row), flush=True)
         del f0, f1, flow, out
+    if args.lc_only:
+        json.dump(res, open(args.out, 'w'), indent=1)
+        return
     # global match
     f0, f1, _ = synth.scale_inputs(Hs, 64, 32, 32, gen, dev)
     for name, kw in (("tc_3xtf32", dict(precision=0)), ("tc_tf32", dict(precision=1)), ("simt", dict(algo=1))):
