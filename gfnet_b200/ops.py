@@ -22,7 +22,15 @@ ALGO_AUTO, ALGO_GENERIC, ALGO_STREAM = 0, 1, 2
 # tuning variants (algo = base | variant << 4 | column-divisor override << 8 | quad-row override << 12)
 ALGO_STREAM_P1 = 2 | (1 << 4)       # one lattice point per thread
 ALGO_QUAD_LDS128 = 2 | (8 << 4)     # 4 points per lane, FFMA2, 16-byte aligned segments
-ALGO_QUAD_LDS64 = 2 | (9 << 4)      # same, 8-byte aligned segments (default)
+ALGO_QUAD_LDS64 = 2 | (9 << 4)      # same, 8-byte aligned segments
+ALGO_TC = 3                         # tcgen05 banded-GEMM kernel (bf16 hi/lo split); algo = 3 | tune << 4
+
+_TC_SHAPES = {(2, 16), (4, 32), (6, 64), (7, 64)}   # (r, C) instantiated in csrc/local_corr_tc.cu
+
+
+def _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
+    return (win_h == hs and win_w == ws and sample_mode == "bilinear" and padding_mode == "zeros"
+            and (r, c) in _TC_SHAPES)
 
 
 def local_correlation(featuremap_size, feature0, feature1, local_radius, num_grid,
@@ -68,6 +76,22 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
         for level in range(num_level):
             hs, ws = int(f1.shape[2]), int(f1.shape[3])
             src, pitch = f1, 0
+            base = int(algo) & 15
+            if base == ALGO_TC or (base == ALGO_AUTO and int(algo) == 0 and _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode)):
+                if not _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
+                    raise NotImplementedError("local_correlation: the tcgen05 kernel covers bilinear/zeros with (r, C) in "
+                                              f"{sorted(_TC_SHAPES)}, got r={r}, C={c}")
+                nws = int(lib.gfb_local_corr_tc_workspace_bytes(B, G))
+                wsbuf = torch.empty(nws, device=f0.device, dtype=torch.uint8)
+                rc = lib.gfb_local_corr_tc_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r,
+                                               kk * num_level, kk * level, int(algo) >> 4 if base == ALGO_TC else 0,
+                                               ptr(wsbuf), nws, st)
+                check(rc, "local_correlation (tcgen05)")
+                if level + 1 < num_level:
+                    nxt = torch.empty((B, c, hs // 2, ws // 2), device=f1.device, dtype=f1.dtype)
+                    check(lib.gfb_avg_pool2_f32(ptr(f1), ptr(nxt), B * c, hs, ws, st), "avg_pool2")
+                    f1 = nxt
+                continue
             if ws % 4 and (int(algo) & 15) != ALGO_GENERIC and _stream_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
                 # TMA needs 16-byte global strides: pad each row once (e.g. ws = 70 -> pitch 72)
                 pitch = (ws + 3) // 4 * 4

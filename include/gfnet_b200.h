@@ -62,6 +62,19 @@ int gfb_local_corr_f32(const float* f0, const float* f1, const float* flow, floa
                        int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                        int win_h, int win_w, int sample_mode, int padding_mode,
                        int k_total, int k_offset, int algo, gfb_stream_t stream);
+/* Tensor-core variant of gfb_local_corr_f32 for the shapes of the matching pyramid (bilinear, zeros padding,
+ * window == (Ws,Hs); (r, C) in {(2,16), (4,32), (6,64), (7,64)}; any Ws/pitch, no alignment requirement).
+ * The correlation is a banded GEMM on tcgen05: f0 / f1 are split into bf16 hi + lo on the fly and
+ * hi*hi + hi*lo + lo*hi is accumulated in fp32 (relative error ~1e-5, inside the 1e-4 fp32 bar).  Tiles whose
+ * windows spread wider than the staged box (wild flow) use exact per-sample gathers.
+ *   workspace: >= gfb_local_corr_tc_workspace_bytes(B, G) bytes of device memory (per-tile plan, written by the
+ *   call); tune 0 = defaults (bits 0-7 tile columns, 8-11 converter warps, 12-15 accumulator columns / 64).
+ * Returns GFB_EUNSUPPORTED for other (r, C): callers then use gfb_local_corr_f32. */
+size_t gfb_local_corr_tc_workspace_bytes(int B, int G);
+int gfb_local_corr_tc_f32(const float* f0, const float* f1, const float* flow, float* out,
+                          int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                          int k_total, int k_offset, int tune,
+                          void* workspace, size_t workspace_bytes, gfb_stream_t stream);
 /* F.avg_pool2d(x, 2, 2) on [N,H,W] planes -> [N,H/2,W/2] (local_correlation.py:71). */
 int gfb_avg_pool2_f32(const float* x, float* y, int N, int H, int W, gfb_stream_t stream);
 /* y[rows, pitch] = x[rows, W] with zero fill of the tail of each row. */

@@ -84,6 +84,25 @@ def test_local_correlation_shapes(gf, shape, kind):
         _close(v_out, ref)
 
 
+TC_SHAPES = [s for s in SHAPES if (s[4], s[1]) in {(2, 16), (4, 32), (6, 64), (7, 64)}]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+@pytest.mark.parametrize("kind", ["homography", "adversarial"])
+def test_local_correlation_tcgen05(gf, shape, kind):
+    """tcgen05 banded-GEMM kernel (bf16 hi/lo split, fp32 accumulate) against the oracle, default and tuned tilings."""
+    from gfnet_b200 import synth
+    b, c, hs, G, r = shape
+    gen = torch.Generator(device="cuda").manual_seed(hash(shape) % 10000 + 1)
+    cgen = torch.Generator().manual_seed(11)
+    Hs = [synth.random_homography(cgen) for _ in range(b)]
+    f0, f1, flow = synth.scale_inputs(Hs, c, hs, G, gen, "cuda", adversarial=(kind == "adversarial"))
+    ref = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
+    for tune in (0, 16, 8, 32 | (4 << 8), (2 << 12) if c < 64 else (4 << 12)):
+        out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=3 | (tune << 4))
+        _close(out, ref)
+
+
 def test_local_correlation_stream_kernel_is_used(gf):
     """algo=2 must run the TMA kernel (raises NotImplementedError if the shape is not eligible)."""
     from gfnet_b200 import synth
@@ -115,7 +134,7 @@ def test_local_correlation_edge_flows(gf):
     for shift in (0.0, 2.5, -3.0, 0.999):
         flow = torch.stack((xx + shift, yy - shift), 0)[None].contiguous()
         ref = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
-        for algo in (0, 1, 2, 2 | (1 << 4), 2 | (2 << 4), 2 | (4 << 4), 2 | (8 << 4), 2 | (9 << 4)):
+        for algo in (0, 1, 2, 3, 2 | (1 << 4), 2 | (2 << 4), 2 | (4 << 4), 2 | (8 << 4), 2 | (9 << 4)):
             _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=algo), ref)
 
 
