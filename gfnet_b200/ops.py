@@ -26,6 +26,7 @@ ALGO_QUAD_LDS64 = 2 | (9 << 4)      # same, 8-byte aligned segments
 ALGO_TC = 3                         # tcgen05 banded-GEMM kernel (bf16 hi/lo split); algo = 3 | tune << 4
 
 _TC_SHAPES = {(2, 16), (4, 32), (6, 64), (7, 64)}   # (r, C) instantiated in csrc/local_corr_tc.cu
+_TC_AUTO = {(4, 32), (6, 64), (7, 64)}              # where it beats the CUDA-core kernels (profiles/r1_kbench_tc.json)
 
 
 def _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
@@ -77,7 +78,8 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
             hs, ws = int(f1.shape[2]), int(f1.shape[3])
             src, pitch = f1, 0
             base = int(algo) & 15
-            if base == ALGO_TC or (base == ALGO_AUTO and int(algo) == 0 and _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode)):
+            if base == ALGO_TC or (int(algo) == ALGO_AUTO and (r, c) in _TC_AUTO
+                                   and _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode)):
                 if not _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
                     raise NotImplementedError("local_correlation: the tcgen05 kernel covers bilinear/zeros with (r, C) in "
                                               f"{sorted(_TC_SHAPES)}, got r={r}, C={c}")

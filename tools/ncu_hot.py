@@ -1,6 +1,6 @@
 """Top stall sites of a kernel from an .ncu-rep (SASS page): python tools/ncu_hot.py rep [topN] [kernel-substr]"""
 import csv, io, subprocess, sys
-rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 25; sub = sys.argv[3] if len(sys.argv) > 3 else ''
 txt = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
 lines = txt.splitlines()
 # find header line
@@ -12,7 +12,7 @@ for ln in lines:
         cur['hdr'] = next(csv.reader([ln]))
     elif cur is not None and 'hdr' in cur:
         cur['rows'].append(next(csv.reader([ln])))
-for blk in blocks[:1]:
+for blk in [b for b in blocks if sub in b['name']][:1]:
     h = {k: i for i, k in enumerate(blk['hdr'])}
     rows = blk['rows']
     tot = sum(int(r[h['# Samples']] or 0) for r in rows)
