@@ -25,8 +25,14 @@ ALGO_QUAD_LDS128 = 2 | (8 << 4)     # 4 points per lane, FFMA2, 16-byte aligned 
 ALGO_QUAD_LDS64 = 2 | (9 << 4)      # same, 8-byte aligned segments
 ALGO_TC = 3                         # tcgen05 banded-GEMM kernel (bf16 hi/lo split); algo = 3 | tune << 4
 
+ALGO_PT = 4                         # one point per thread, whole patch in registers (TMA box per CTA); algo = 4 | tune << 4
+ALGO_TC2 = 5                        # tcgen05 banded GEMM fed by TMA from a bf16 hi/lo workspace; algo = 5 | group << 4
+
 _TC_SHAPES = {(2, 16), (4, 32), (6, 64), (7, 64)}   # (r, C) instantiated in csrc/local_corr_tc.cu
-_TC_AUTO = {(4, 32), (6, 64), (7, 64)}              # where it beats the CUDA-core kernels (profiles/r1_kbench_tc.json)
+_TC_AUTO = set()                                    # superseded by the TMA-fed kernels below
+_TC2_SHAPES = {(4, 32), (3, 32), (6, 64), (7, 64), (5, 64), (4, 64)}   # csrc/local_corr_v2.cu
+_PT_SHAPES = {(2, 16), (4, 32), (1, 16), (1, 8), (2, 8)}
+_PT_AUTO = {(2, 16), (1, 16), (1, 8), (2, 8)}
 
 
 def _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
@@ -78,6 +84,38 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
             hs, ws = int(f1.shape[2]), int(f1.shape[3])
             src, pitch = f1, 0
             base = int(algo) & 15
+            plain = _tc_eligible_modes(win_h, win_w, hs, ws, sample_mode, padding_mode)
+            if base == ALGO_TC2 or (int(algo) == ALGO_AUTO and plain and (r, c) in _TC2_SHAPES):
+                if not (plain and (r, c) in _TC2_SHAPES):
+                    raise NotImplementedError("local_correlation: the TMA-fed tcgen05 kernel covers bilinear/zeros with "
+                                              f"(r, C) in {sorted(_TC2_SHAPES)}, got r={r}, C={c}")
+                group = int(algo) >> 4 if base == ALGO_TC2 else 0
+                nws = int(lib.gfb_local_corr_tc2_workspace_bytes(B, c, hs, ws, G, r, group))
+                wsbuf = torch.empty(nws, device=f0.device, dtype=torch.uint8)
+                rc = lib.gfb_local_corr_tc2_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r,
+                                                kk * num_level, kk * level, group, ptr(wsbuf), nws, st)
+                check(rc, "local_correlation (tcgen05, TMA-fed)")
+                if level + 1 < num_level:
+                    nxt = torch.empty((B, c, hs // 2, ws // 2), device=f1.device, dtype=f1.dtype)
+                    check(lib.gfb_avg_pool2_f32(ptr(f1), ptr(nxt), B * c, hs, ws, st), "avg_pool2")
+                    f1 = nxt
+                continue
+            if base == ALGO_PT or (int(algo) == ALGO_AUTO and plain and (r, c) in _PT_AUTO and G % 4 == 0):
+                if not (plain and (r, c) in _PT_SHAPES):
+                    raise NotImplementedError("local_correlation: the point-per-thread kernel covers bilinear/zeros with "
+                                              f"(r, C) in {sorted(_PT_SHAPES)}, got r={r}, C={c}")
+                if ws % 4:
+                    pitch = (ws + 3) // 4 * 4
+                    src = torch.empty((B, c, hs, pitch), device=f1.device, dtype=f1.dtype)
+                    check(lib.gfb_pad_rows_f32(ptr(f1), ptr(src), B * c * hs, ws, pitch, st), "pad_rows")
+                rc = lib.gfb_local_corr_pt_f32(ptr(f0), ptr(src), ptr(fl), ptr(out), B, c, hs, ws, pitch, G, r,
+                                               kk * num_level, kk * level, int(algo) >> 4 if base == ALGO_PT else 0, st)
+                check(rc, "local_correlation (point-per-thread)")
+                if level + 1 < num_level:
+                    nxt = torch.empty((B, c, hs // 2, ws // 2), device=f1.device, dtype=f1.dtype)
+                    check(lib.gfb_avg_pool2_f32(ptr(f1), ptr(nxt), B * c, hs, ws, st), "avg_pool2")
+                    f1 = nxt
+                continue
             if base == ALGO_TC or (int(algo) == ALGO_AUTO and (r, c) in _TC_AUTO
                                    and _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode)):
                 if not _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
@@ -110,9 +148,21 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
     return out
 
 
+def _tc_eligible_modes(win_h, win_w, hs, ws, sample_mode, padding_mode):
+    return win_h == hs and win_w == ws and sample_mode == "bilinear" and padding_mode == "zeros"
+
+
 def _stream_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
     return (win_h == hs and win_w == ws and sample_mode == "bilinear" and padding_mode == "zeros"
             and 1 <= r <= 8 and c % 16 == 0 and (c in (16, 32) or c % 64 == 0))
+
+
+def local_correlation_v2_counters(reset=True):
+    """(lc_pt points on the global-memory path, lc_tc2 points on the gather path, lc_tc2 gather tiles, 0); synchronises."""
+    import ctypes
+    buf = (ctypes.c_ulonglong * 4)()
+    check(lib.gfb_debug_local_corr_v2_counters(buf, int(reset)), "counters")
+    return tuple(int(v) for v in buf)
 
 
 def local_correlation_counters(reset=True):
@@ -221,4 +271,5 @@ def global_match_flops(B, C, N0, N1):
 
 
 __all__ = ["local_correlation", "kde", "coarse_match", "corr_volume", "pos_embed", "LazyCorrVolume",
-           "local_correlation_bytes", "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_STREAM"]
+           "local_correlation_bytes", "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_STREAM", "ALGO_TC",
+           "ALGO_PT", "ALGO_TC2"]

@@ -75,6 +75,31 @@ int gfb_local_corr_tc_f32(const float* f0, const float* f1, const float* flow, f
                           int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                           int k_total, int k_offset, int tune,
                           void* workspace, size_t workspace_bytes, gfb_stream_t stream);
+/* Second-generation kernels for the same operator (utils/local_correlation.py:4-72; bilinear, zero padding, window
+ * == (Ws,Hs) only -- the configuration GFNet uses, model/network.py:553-554).  Same tensors as gfb_local_corr_f32.
+ *
+ * gfb_local_corr_pt_f32: one lattice point per thread, the whole (2r+2)^2 integer patch of dot products in registers,
+ *   f1 staged per CTA by one TMA box per 4 channels (zero fill outside the image).  (r, C) in {(2,16), (4,32), (1,16),
+ *   (1,8), (2,8)}; f1_pitch % 4 == 0, f0 / f1 16-byte aligned (TMA strides) else GFB_EALIGN; G % 4 == 0 else
+ *   GFB_EUNSUPPORTED.  tune 0 = auto box size.
+ *
+ * gfb_local_corr_tc2_f32: banded GEMM on tcgen05 fed by TMA.  A pre-pass rewrites f0 / f1 once as position-major
+ *   rows [bf16 hi(C) | bf16 lo(C)] into `workspace` (processed in groups of `group` batch elements so that the
+ *   workspace stays L2-resident; 0 = auto), the main kernel accumulates hi*hi + hi*lo + lo*hi in fp32 (relative error
+ *   ~1e-5, inside the 1e-4 fp32 bar).  (r, C) in {(4,32), (3,32), (6,64), (7,64), (5,64), (4,64)}; any Ws / pitch.
+ *   workspace >= gfb_local_corr_tc2_workspace_bytes(...) bytes, 128-byte aligned.
+ * Both return GFB_EUNSUPPORTED for other (r, C); points whose windows leave the staged box use the exact gather. */
+int gfb_local_corr_pt_f32(const float* f0, const float* f1, const float* flow, float* out,
+                          int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                          int k_total, int k_offset, int tune, gfb_stream_t stream);
+size_t gfb_local_corr_tc2_workspace_bytes(int B, int C, int Hs, int Ws, int G, int r, int group);
+/* Debug aid (synchronises): host_out4 = {lc_pt points on the global-memory path, lc_tc2 points on the gather path,
+ * lc_tc2 gather tiles, 0}; reset != 0 zeroes. */
+int gfb_debug_local_corr_v2_counters(unsigned long long* host_out4, int reset);
+int gfb_local_corr_tc2_f32(const float* f0, const float* f1, const float* flow, float* out,
+                           int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                           int k_total, int k_offset, int group,
+                           void* workspace, size_t workspace_bytes, gfb_stream_t stream);
 /* F.avg_pool2d(x, 2, 2) on [N,H,W] planes -> [N,H/2,W/2] (local_correlation.py:71). */
 int gfb_avg_pool2_f32(const float* x, float* y, int N, int H, int W, gfb_stream_t stream);
 /* y[rows, pitch] = x[rows, W] with zero fill of the tail of each row. */

@@ -103,6 +103,35 @@ def test_local_correlation_tcgen05(gf, shape, kind):
         _close(out, ref)
 
 
+V2_SHAPES = SHAPES + [(3, 16, 224, 128, 2), (1, 16, 96, 96, 2), (1, 32, 100, 50, 4), (3, 64, 70, 40, 6), (1, 64, 84, 48, 6)]
+
+
+@pytest.mark.parametrize("shape", V2_SHAPES)
+@pytest.mark.parametrize("kind", ["homography", "adversarial"])
+def test_local_correlation_v2_kernels(gf, shape, kind):
+    """TMA-fed kernels (csrc/local_corr_v2.cu): point-per-thread (C = 16) and tcgen05 banded GEMM (C >= 32) against
+    the oracle; the tcgen05 kernel also with 1- and 2-element workspace groups."""
+    from gfnet_b200 import synth
+    from gfnet_b200.ops import ALGO_PT, ALGO_TC2
+    b, c, hs, G, r = shape
+    gen = torch.Generator(device="cuda").manual_seed(hash(shape) % 10000 + 5)
+    cgen = torch.Generator().manual_seed(13)
+    Hs = [synth.random_homography(cgen) for _ in range(b)]
+    f0, f1, flow = synth.scale_inputs(Hs, c, hs, G, gen, "cuda", adversarial=(kind == "adversarial"))
+    ref = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
+    if (r, c) in {(2, 16), (4, 32)}:
+        for tune in (0, 1, 2, 3, 4):
+            try:
+                out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=ALGO_PT | (tune << 4))
+            except NotImplementedError:
+                assert G % 4 != 0          # the f0 tensor map needs 16-byte row strides
+                continue
+            _close(out, ref)
+    if c >= 32:
+        for group in (0, 1, 2):
+            _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=ALGO_TC2 | (group << 4)), ref)
+
+
 def test_local_correlation_stream_kernel_is_used(gf):
     """algo=2 must run the TMA kernel (raises NotImplementedError if the shape is not eligible)."""
     from gfnet_b200 import synth
@@ -134,7 +163,7 @@ def test_local_correlation_edge_flows(gf):
     for shift in (0.0, 2.5, -3.0, 0.999):
         flow = torch.stack((xx + shift, yy - shift), 0)[None].contiguous()
         ref = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
-        for algo in (0, 1, 2, 3, 2 | (1 << 4), 2 | (2 << 4), 2 | (4 << 4), 2 | (8 << 4), 2 | (9 << 4)):
+        for algo in (0, 1, 2, 3, 5, 2 | (1 << 4), 2 | (2 << 4), 2 | (4 << 4), 2 | (8 << 4), 2 | (9 << 4)):
             _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=algo), ref)
 
 

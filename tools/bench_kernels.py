@@ -63,10 +63,12 @@ def main():
                                    iters=5 if algo == 1 else 10, flush=flush)
             except NotImplementedError:
                 continue
-            from gfnet_b200.ops import local_correlation_counters
+            from gfnet_b200.ops import local_correlation_counters, local_correlation_v2_counters
             local_correlation_counters(reset=True)
+            local_correlation_v2_counters(reset=True)
             gf.local_correlation((b, c, hs, hs), f0, f1, r, g, flow=flow, algo=algo, out=out)
             cnt = local_correlation_counters(reset=True)
+            cnt = list(cnt) + list(local_correlation_v2_counters(reset=True))
             row = dict(scale=s, c=c, hs=hs, G=g, r=r, algo=algo, ms=med, ms_best=best, GBps=nbytes / med / 1e6, counters=cnt,
                        frac=nbytes / med / 1e6 / PEAK_HBM, fma_T=(b * c * (2 * r + 2) ** 2 * g * g) / med / 1e9)
             res["local_corr"].append(row)
