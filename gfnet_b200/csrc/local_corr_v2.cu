@@ -905,6 +905,14 @@ extern "C" size_t gfb_local_corr_tc2_workspace_bytes(int B, int C, int Hs, int W
            lcv2::align_up(gb * ws0_per, 1024) + gb * ws1_per;
 }
 
+// number of (pre-pass, main) launch pairs gfb_local_corr_tc2_f32 issues for these shapes (bench.py's launch count)
+extern "C" int gfb_local_corr_tc2_groups(int B, int C, int Hs, int Ws, int G, int group) {
+    if (B <= 0 || C <= 0 || Hs <= 0 || Ws <= 0 || G <= 0) return 0;
+    const size_t per = (size_t)G * G * C * 4 + (size_t)Hs * Ws * C * 4;
+    const int gb = lcv2::tc2_group(B, per, group);
+    return (B + gb - 1) / gb;
+}
+
 extern "C" int gfb_local_corr_tc2_f32(const float* f0, const float* f1, const float* flow, float* out,
                                       int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                                       int k_total, int k_offset, int group,

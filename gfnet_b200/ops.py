@@ -261,6 +261,16 @@ def pos_embed(corr):
     return flow
 
 
+def local_correlation_launches(B, c, hs, ws, G, r):
+    """Kernels one default-mode local_correlation call launches for a GFNet-style call (bilinear, zeros, window = f1)."""
+    if (r, c) in _TC2_SHAPES:
+        return 2 * int(lib.gfb_local_corr_tc2_groups(B, c, hs, ws, G, 0))     # fused pre-pass + plan, main kernel
+    n = 1
+    if ws % 4 and ((r, c) in _PT_AUTO or _stream_eligible(c, r, hs, ws, hs, ws, "bilinear", "zeros")):
+        n += 1                                                                # pad_rows
+    return n
+
+
 def local_correlation_bytes(B, c, hs, ws, G, r):
     """Algorithmic HBM bytes of one call: read f0, f1, flow once, write corr once."""
     return 4 * B * (c * G * G + c * hs * ws + 2 * G * G + (2 * r + 1) ** 2 * G * G)
@@ -271,5 +281,5 @@ def global_match_flops(B, C, N0, N1):
 
 
 __all__ = ["local_correlation", "kde", "coarse_match", "corr_volume", "pos_embed", "LazyCorrVolume",
-           "local_correlation_bytes", "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_STREAM", "ALGO_TC",
+           "local_correlation_bytes", "local_correlation_launches", "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_STREAM", "ALGO_TC",
            "ALGO_PT", "ALGO_TC2"]

@@ -27,7 +27,10 @@ class HotPath:
     def kernel_launches(self, batch):
         """How many of our kernels one run() launches (bench.py's gpu_launches claim)."""
         n = 1                                                   # global match
-        n += sum(len(sc["flows"]) for p in batch.passes for sc in p)   # local_corr
+        for p in batch.passes:                                  # local_corr: 1 launch (point kernel) or 2 per workspace group
+            for sc in p:
+                b = sc["f1"].shape[0]
+                n += len(sc["flows"]) * ops.local_correlation_launches(b, sc["c"], sc["hs"], sc["hs"], sc["G"], sc["r"])
         n += 1 + 1 + 1 + 1 + 1 + 1 + 1 + 1                      # postprocess, keys, topk, gather, kde, balance, topk, gather
         n += (2 if self.n_hyp > 0 else 0) + 1 + 1               # init+ransac, refit, corner error
         return n

@@ -93,6 +93,8 @@ int gfb_local_corr_pt_f32(const float* f0, const float* f1, const float* flow, f
                           int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                           int k_total, int k_offset, int tune, gfb_stream_t stream);
 size_t gfb_local_corr_tc2_workspace_bytes(int B, int C, int Hs, int Ws, int G, int r, int group);
+/* how many (pre-pass, main) launch pairs one gfb_local_corr_tc2_f32 call issues for these shapes */
+int gfb_local_corr_tc2_groups(int B, int C, int Hs, int Ws, int G, int group);
 /* Debug aid (synchronises): host_out4 = {lc_pt points on the global-memory path, lc_tc2 points on the gather path,
  * lc_tc2 gather tiles, 0}; reset != 0 zeroes. */
 int gfb_debug_local_corr_v2_counters(unsigned long long* host_out4, int reset);
