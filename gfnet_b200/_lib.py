@@ -13,7 +13,7 @@ EXPORTS = [
     "gfb_abi_version", "gfb_strerror", "gfb_device_info", "gfb_local_corr_f32", "gfb_avg_pool2_f32",
     "gfb_pad_rows_f32", "gfb_debug_local_corr_counters", "gfb_local_corr_tc_workspace_bytes", "gfb_local_corr_tc_f32", "gfb_local_corr_pt_f32",
     "gfb_local_corr_tc2_workspace_bytes", "gfb_local_corr_tc2_f32", "gfb_debug_local_corr_v2_counters", "gfb_local_corr_tc2_groups",
-    "gfb_global_match_f32", "gfb_pos_embed_f32", "gfb_kde_f32", "gfb_match_postprocess_f32",
+    "gfb_global_match_f32", "gfb_pos_embed_f32", "gfb_kde_f32", "gfb_kde_sym_workspace_bytes", "gfb_kde_sym_f32", "gfb_match_postprocess_f32",
     "gfb_sample_keys_f32", "gfb_balance_keys_f32", "gfb_gather_matches_f32", "gfb_topk_workspace_bytes",
     "gfb_topk_desc_f32", "gfb_homography_workspace_bytes", "gfb_homography_f32", "gfb_corner_error_f64",
 ]
@@ -54,6 +54,9 @@ def _load():
     lib.gfb_global_match_f32.argtypes = [vp, vp, vp, vp] + [i32] * 8 + [vp]
     lib.gfb_pos_embed_f32.argtypes = [vp, vp] + [i32] * 5 + [vp]
     lib.gfb_kde_f32.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
+    lib.gfb_kde_sym_workspace_bytes.restype = sz
+    lib.gfb_kde_sym_workspace_bytes.argtypes = [i32, i32]
+    lib.gfb_kde_sym_f32.argtypes = [vp, vp, i32, i32, f32, vp, sz, vp]
     lib.gfb_match_postprocess_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.gfb_sample_keys_f32.argtypes = [vp, vp, vp, i64, f32, vp]
     lib.gfb_balance_keys_f32.argtypes = [vp, vp, vp, i64, f32, vp]
@@ -67,7 +70,8 @@ def _load():
     lib.gfb_corner_error_f64.argtypes = [vp, vp, vp, i32, f32, f32, f32, vp]
     for name in EXPORTS:   # getattr raises AttributeError if the library lacks a declared symbol
         if name not in ("gfb_strerror", "gfb_topk_workspace_bytes", "gfb_homography_workspace_bytes",
-                        "gfb_local_corr_tc_workspace_bytes", "gfb_local_corr_tc2_workspace_bytes"):
+                        "gfb_local_corr_tc_workspace_bytes", "gfb_local_corr_tc2_workspace_bytes",
+                        "gfb_kde_sym_workspace_bytes"):
             getattr(lib, name).restype = i32
     if lib.gfb_abi_version() != 1:
         raise ImportError("libgfnet_b200.so ABI version mismatch; rebuild with `make -C gfnet_b200/csrc`")

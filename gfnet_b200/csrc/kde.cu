@@ -124,6 +124,147 @@ __global__ void __launch_bounds__(KDE_THREADS) kde4_kernel(const float* __restri
         if (row[r] < M) density[(size_t)b * M + row[r]] = acc[r];
 }
 
+// ---- symmetric variant (down == 1: y = x) ---------------------------------------------------------------------
+// K(x_i, x_j) = K(x_j, x_i), so only the tile pairs (I, J >= I) of 128 x 128 points are evaluated and every value is
+// added to the density of its row AND of its column: half the ex2 evaluations.  A CTA owns row block I and up to
+// KS_JC column blocks; a thread keeps an 8 x 8 register tile (rows ti*8.., columns tj*8..).  Row sums stay in
+// registers until the CTA ends; column sums are folded over the 16 lanes that share the columns with a shuffle
+// transpose-reduce after every tile pair.  Partial sums meet in a 64-bit fixed-point accumulator (2^-40 units):
+// integer atomics are order-independent, so the density is deterministic although CTAs finish in any order.
+constexpr int KS_T = 128;
+constexpr int KS_JC = 16;
+constexpr int KS_PITCH = 16 * 9;
+constexpr float KS_FIX = 1099511627776.f;   // 2^40
+
+__device__ __forceinline__ unsigned long long kde_fix(float v) { return __float2ull_rn(v * KS_FIX); }
+
+__global__ void __launch_bounds__(256, 3) kde4_sym_kernel(const float* __restrict__ x, unsigned long long* __restrict__ acc64,
+                                                          int M, int nb, float scale) {
+    // column block, 8 points per tj at a pitch of 9: the two half-warps of a warp (tj, tj + 1) read different banks
+    __shared__ float4 sy[2][KS_PITCH];          // 2 * y'
+    __shared__ float sn[2][KS_PITCH];           // -|y'|^2
+    __shared__ float srow[16][KS_T];            // end of the CTA: row sums of the 16 column groups
+    const int I = blockIdx.x, b = blockIdx.z;
+    const int j0 = I + blockIdx.y * KS_JC;
+    if (j0 >= nb) return;
+    const int j1 = min(j0 + KS_JC, nb);
+    const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
+    const float4* xb = reinterpret_cast<const float4*>(x) + (size_t)b * M;
+
+    unsigned long long x2[4][4], nn2[4], rs2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 v[2];
+        float nn[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = I * KS_T + ti * 8 + 2 * q + h;
+            float4 w = row < M ? __ldg(xb + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w.x *= scale; w.y *= scale; w.z *= scale; w.w *= scale;
+            v[h] = w;
+            nn[h] = row < M ? -(w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w) : -3.0e38f;   // masked row: ex2(-inf) = 0
+        }
+        x2[q][0] = kpack2(v[0].x, v[1].x);
+        x2[q][1] = kpack2(v[0].y, v[1].y);
+        x2[q][2] = kpack2(v[0].z, v[1].z);
+        x2[q][3] = kpack2(v[0].w, v[1].w);
+        nn2[q] = kpack2(nn[0], nn[1]);
+        rs2[q] = 0ull;
+    }
+    auto put = [&](int buf, int i, int idx, float4 v) {
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        const int k = (i >> 3) * 9 + (i & 7);
+        sn[buf][k] = idx < M ? -(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w) : -3.0e38f;
+        sy[buf][k] = make_float4(2.f * v.x, 2.f * v.y, 2.f * v.z, 2.f * v.w);
+    };
+    if (tid < KS_T) {
+        const int idx = j0 * KS_T + tid;
+        put(0, tid, idx, idx < M ? __ldg(xb + idx) : make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    __syncthreads();
+    for (int J = j0; J < j1; ++J) {
+        const int buf = (J - j0) & 1;
+        // the upper half of the CTA fetches the next column block while everybody computes on this one
+        const bool pf = tid >= KS_T && J + 1 < j1;
+        const int pidx = (J + 1) * KS_T + tid - KS_T;
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pf && pidx < M) pv = __ldg(xb + pidx);
+        unsigned long long cs2[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            const float4 y = sy[buf][tj * 9 + cc];
+            const float ny = sn[buf][tj * 9 + cc];
+            const unsigned long long y0 = kpack2(y.x, y.x), y1 = kpack2(y.y, y.y), y2 = kpack2(y.z, y.z), y3 = kpack2(y.w, y.w);
+            const unsigned long long nyy = kpack2(ny, ny);
+            unsigned long long csum = 0ull;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                unsigned long long t = kadd2(nn2[q], nyy);
+                t = kfma2(x2[q][0], y0, t);
+                t = kfma2(x2[q][1], y1, t);
+                t = kfma2(x2[q][2], y2, t);
+                t = kfma2(x2[q][3], y3, t);
+                float t0, t1;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+                const unsigned long long e = kpack2(ex2_approx(t0), ex2_approx(t1));
+                rs2[q] = kadd2(rs2[q], e);
+                csum = kadd2(csum, e);
+            }
+            cs2[cc] = csum;
+        }
+        if (J != I) {                            // the diagonal tile is a full square: its row sums already hold everything
+            float cs[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                float lo, hi;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(cs2[cc]));
+                cs[cc] = lo + hi;
+            }
+            // fold over the 16 lanes (ti) that share these 8 columns: transpose-reduce, 8 -> 4 -> 2 -> 1 values per lane
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float send = (ti & 1) ? cs[k] : cs[k + 4], keep = (ti & 1) ? cs[k + 4] : cs[k];
+                cs[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float send = (ti & 2) ? cs[k] : cs[k + 2], keep = (ti & 2) ? cs[k + 2] : cs[k];
+                cs[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            {
+                const float send = (ti & 4) ? cs[0] : cs[1], keep = (ti & 4) ? cs[1] : cs[0];
+                cs[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            cs[0] += __shfl_xor_sync(0xffffffffu, cs[0], 8);
+            const int col = 4 * (ti & 1) + 2 * ((ti >> 1) & 1) + ((ti >> 2) & 1);
+            const int idx = J * KS_T + tj * 8 + col;
+            if (ti < 8 && idx < M) atomicAdd(acc64 + (size_t)b * M + idx, kde_fix(cs[0]));
+        }
+        if (pf) put(buf ^ 1, tid - KS_T, pidx, pv);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(rs2[q]));
+        srow[tj][ti * 8 + 2 * q] = lo;
+        srow[tj][ti * 8 + 2 * q + 1] = hi;
+    }
+    __syncthreads();
+    if (tid < KS_T) {
+        const int idx = I * KS_T + tid;
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) sum += srow[g][tid];          // fixed order: deterministic
+        if (idx < M) atomicAdd(acc64 + (size_t)b * M + idx, kde_fix(sum));
+    }
+}
+
+__global__ void __launch_bounds__(256) kde_finish_kernel(const unsigned long long* __restrict__ acc64, float* __restrict__ density, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        density[i] = (float)((double)acc64[i] * (1.0 / 1099511627776.0));
+}
+
 // Any D <= 8 (not on the GFNet path; kept so the op is a full drop-in for kde(x) with other widths).
 __global__ void __launch_bounds__(KDE_THREADS) kde_generic_kernel(const float* __restrict__ x, float* __restrict__ density,
                                                                   int M, int Mp, int D, int down, float scale) {
@@ -145,6 +286,32 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_generic_kernel(const float* _
 }  // namespace gfb
 
 using namespace gfb;
+
+extern "C" size_t gfb_kde_sym_workspace_bytes(int B, int M) {
+    return B > 0 && M > 0 ? (size_t)B * M * sizeof(unsigned long long) : 0;
+}
+
+// kde(x) with y = x (down == 1), D = 4: symmetric evaluation, see kde4_sym_kernel.
+extern "C" int gfb_kde_sym_f32(const float* x, float* density, int B, int M, float std,
+                               void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
+    GFB_CHECK_ARG(x && density && B > 0 && M > 0 && std > 0.f);
+    GFB_CHECK_ARG(B <= 65535);
+    if (!gfb_aligned(x, 16) || !gfb_aligned(workspace, 8)) return GFB_EALIGN;
+    const size_t need = (size_t)B * M * sizeof(unsigned long long);
+    if (!workspace || workspace_bytes < need) return GFB_EWORKSPACE;
+    const float scale = (float)sqrt(1.4426950408889634 / (2.0 * (double)std * (double)std));
+    cudaStream_t st = gfb_cu(stream);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
+    if (e != cudaSuccess) return (int)e;
+    const int nb = (M + KS_T - 1) / KS_T;
+    if (nb > 65535) return GFB_EUNSUPPORTED;
+    dim3 grid((unsigned)nb, (unsigned)((nb + KS_JC - 1) / KS_JC), (unsigned)B);
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(workspace);
+    kde4_sym_kernel<<<grid, 256, 0, st>>>(x, acc, M, nb, scale);
+    const size_t n = (size_t)B * M;
+    kde_finish_kernel<<<(unsigned)min((size_t)148 * 8, (n + 255) / 256), 256, 0, st>>>(acc, density, n);
+    GFB_LAUNCH_RESULT();
+}
 
 extern "C" int gfb_kde_f32(const float* x, float* density, int B, int M, int D, int down, float std,
                            gfb_stream_t stream) {

@@ -173,7 +173,10 @@ def local_correlation_counters(reset=True):
     return tuple(int(v) for v in buf)
 
 
-def kde(x, std=0.1, half=True, down=None):
+KDE_AUTO, KDE_FULL, KDE_SYMMETRIC = 0, 1, 2
+
+
+def kde(x, std=0.1, half=True, down=None, *, algo=KDE_AUTO):
     """Gaussian kernel density of the rows of ``x [M,D]`` (or batched ``[B,M,D]``).
 
     reference: utils/kde.py:4-13.  Arithmetic is fp32 (the parity target is the reference's
@@ -190,8 +193,17 @@ def kde(x, std=0.1, half=True, down=None):
     xb = xin if batched else xin[None]
     B, M, D = (int(v) for v in xb.shape)
     dens = torch.empty((B, M), device=xb.device, dtype=torch.float32)
+    dn = 1 if down is None else int(down)
+    sym_ok = D == 4 and dn == 1
+    if algo == KDE_SYMMETRIC and not sym_ok:
+        raise NotImplementedError("kde: the symmetric kernel needs D = 4 and down = 1 (y = x)")
     with torch.cuda.device(xb.device):
-        rc = lib.gfb_kde_f32(ptr(xb), ptr(dens), B, M, D, 1 if down is None else int(down), float(std), stream_ptr(xb.device))
+        if algo == KDE_SYMMETRIC or (algo == KDE_AUTO and sym_ok and M >= 2048):
+            nws = int(lib.gfb_kde_sym_workspace_bytes(B, M))
+            wsbuf = torch.empty(nws, device=xb.device, dtype=torch.uint8)
+            rc = lib.gfb_kde_sym_f32(ptr(xb), ptr(dens), B, M, float(std), ptr(wsbuf), nws, stream_ptr(xb.device))
+        else:
+            rc = lib.gfb_kde_f32(ptr(xb), ptr(dens), B, M, D, dn, float(std), stream_ptr(xb.device))
     check(rc, "kde")
     dens = dens if batched else dens[0]
     return dens.half() if half else dens

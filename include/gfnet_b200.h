@@ -134,6 +134,13 @@ int gfb_pos_embed_f32(const float* vol, float* flow_out, int B, int H0, int W0, 
  * fp32 throughout (the parity target is the reference's half=False path). */
 int gfb_kde_f32(const float* x, float* density, int B, int M, int D, int down, float std,
                 gfb_stream_t stream);
+/* Same operator for the configuration the reference uses on CUDA (down = 1, i.e. y = x; D = 4; model/network.py:405-408):
+ * the kernel is symmetric, so only tile pairs (I, J >= I) are evaluated and every value is added to its row and its
+ * column -- half the exponentials.  Sums meet in a 64-bit fixed-point accumulator (deterministic).
+ *   workspace >= gfb_kde_sym_workspace_bytes(B, M) bytes, 8-byte aligned; zeroed by the call. */
+size_t gfb_kde_sym_workspace_bytes(int B, int M);
+int gfb_kde_sym_f32(const float* x, float* density, int B, int M, float std,
+                    void* workspace, size_t workspace_bytes, gfb_stream_t stream);
 
 /* ---- match post-process (tail of GFNet.match, model/network.py:358-384) -----------------------
  *   flow [b,2,G,G], cert_logits [b,1,G,G], attenuation [b,1,G,G] or NULL (the low_res_certainty

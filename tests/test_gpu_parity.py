@@ -242,6 +242,28 @@ def test_kde_golden_and_sizes(gf, golden):
     assert gf.kde(x, 0.1, half=True).dtype == torch.float16
 
 
+def test_kde_symmetric_kernel(gf):
+    """down = 1: the symmetric kernel (half the exponentials, fixed-point accumulation) against the oracle and the full
+    kernel; sizes off the 128-point block grid; run-to-run deterministic."""
+    from gfnet_b200 import synth
+    from gfnet_b200.ops import KDE_FULL, KDE_SYMMETRIC
+    gen = torch.Generator(device="cuda").manual_seed(15)
+    cgen = torch.Generator().manual_seed(16)
+    for m in (20000, 5000, 2177, 128, 129, 1):
+        x = synth.make_matches(synth.random_homography(cgen), m, gen, "cuda")
+        ref = oracle.kde_def(x.cpu(), 0.1)
+        a = gf.kde(x, 0.1, half=False, algo=KDE_SYMMETRIC)
+        _close(a, ref, rtol=1e-4, atol_rel=0)
+        _close(a, gf.kde(x, 0.1, half=False, algo=KDE_FULL), rtol=2e-5, atol_rel=0)
+        assert torch.equal(a, gf.kde(x, 0.1, half=False, algo=KDE_SYMMETRIC))
+    xb = torch.stack([synth.make_matches(synth.random_homography(cgen), 3333, gen, "cuda") for _ in range(3)])
+    outb = gf.kde(xb, 0.1, half=False, algo=KDE_SYMMETRIC)
+    for i in range(3):
+        _close(outb[i], oracle.kde_def(xb[i].cpu(), 0.1), rtol=1e-4, atol_rel=0)
+    with pytest.raises(NotImplementedError):
+        gf.kde(xb, 0.1, half=False, down=8, algo=KDE_SYMMETRIC)
+
+
 def test_match_postprocess(gf):
     gen = torch.Generator().manual_seed(3)
     for B, G, sym in ((2, 16, True), (1, 40, True), (3, 8, False)):

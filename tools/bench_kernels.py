@@ -86,9 +86,13 @@ def main():
     # kde
     Bp = max(1, b // 2)
     x = torch.stack([synth.make_matches(Hs[i], 20000, gen, dev) for i in range(Bp)])
-    med, best = timeit(lambda: gf.kde(x, 0.1, half=False), iters=5, flush=flush)
-    res["other"]["kde_M20000"] = dict(ms=med, ms_best=best, pairs=Bp, Gevals_per_s=Bp * 4e8 / med / 1e6,
-                                      mufu_frac=Bp * 4e8 / med / 1e6 / 4654.0)
+    from gfnet_b200.ops import KDE_FULL, KDE_SYMMETRIC
+    med, best = timeit(lambda: gf.kde(x, 0.1, half=False, algo=KDE_FULL), iters=5, flush=flush)
+    res["other"]["kde_M20000_full"] = dict(ms=med, ms_best=best, pairs=Bp, Gevals_per_s=Bp * 4e8 / med / 1e6,
+                                           mufu_frac=Bp * 4e8 / med / 1e6 / 4654.0)
+    med, best = timeit(lambda: gf.kde(x, 0.1, half=False, algo=KDE_SYMMETRIC), iters=5, flush=flush)
+    res["other"]["kde_M20000_symmetric"] = dict(ms=med, ms_best=best, pairs=Bp, Gentries_per_s=Bp * 4e8 / med / 1e6,
+                                                mufu_frac_of_evaluated_half=Bp * 2e8 / med / 1e6 / 4654.0)
     x1 = x[:1].contiguous()
     med, best = timeit(lambda: gf.kde(x1, 0.1, half=False), iters=5)
     res["other"]["kde_M20000_single_pair"] = dict(ms=med, ms_best=best)
