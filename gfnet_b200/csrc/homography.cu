@@ -72,11 +72,12 @@ __device__ bool solve8(double (&M)[8][9]) {
 }
 
 constexpr int RS_THREADS = 128;
+constexpr int RS_SPLIT = 8;        // threads per hypothesis: each scores every RS_SPLIT-th point (fp64 scoring is latency-bound)
 
 __global__ void __launch_bounds__(RS_THREADS) ransac_kernel(HgParams p) {
     extern __shared__ float4 spts[];   // pixel coords (ax, ay, bx, by) of all N points of this pair
     const int b = blockIdx.y;
-    const int hyp = blockIdx.x * RS_THREADS + threadIdx.x;
+    const int hyp = (blockIdx.x * RS_THREADS + threadIdx.x) / RS_SPLIT, sub = threadIdx.x % RS_SPLIT;
     const float4* mb = reinterpret_cast<const float4*>(p.matches) + (size_t)b * p.N;
     for (int i = threadIdx.x; i < p.N; i += RS_THREADS) {
         float4 m = __ldg(mb + i), q;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_kernel(HgParams p) {
         spts[i] = q;
     }
     __syncthreads();
-    if (hyp >= p.n_hyp) return;
+    if (hyp >= p.n_hyp) return;        // n_hyp * RS_SPLIT is a multiple of 32 or the tail warp exits as a whole group
     // four distinct indices from a counter-based hash (oracle.estimation.minimal_sample)
     int idx[4];
     {
@@ -114,10 +115,11 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_kernel(HgParams p) {
     for (int e = 0; e < 8; ++e) { h[e] = M[e][8]; ok = ok && isfinite(h[e]); }
     h[8] = 1.0;
     double* hs = p.hyp_H + ((size_t)b * p.n_hyp + hyp) * 9;
-    for (int e = 0; e < 9; ++e) hs[e] = ok ? h[e] : 0.0;
-    if (!ok) return;
+    if (sub == 0)
+        for (int e = 0; e < 9; ++e) hs[e] = ok ? h[e] : 0.0;
+    if (!ok) return;                   // the same decision in all RS_SPLIT threads of the hypothesis
     int cnt = 0;
-    for (int i = 0; i < p.N; ++i) {
+    for (int i = sub; i < p.N; i += RS_SPLIT) {
         const float4 q = spts[i];
         const double X = q.x, Y = q.y;
         const double ww = 1.0 / (h[6] * X + h[7] * Y + 1.0);
@@ -125,6 +127,11 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_kernel(HgParams p) {
         const double dy = (h[3] * X + h[4] * Y + h[5]) * ww - (double)q.w;
         cnt += (dx * dx + dy * dy <= (double)p.thr2);
     }
+    // the RS_SPLIT threads of a hypothesis are consecutive lanes of one warp
+    const unsigned gmask = ((1u << RS_SPLIT) - 1u) << ((threadIdx.x & 31) / RS_SPLIT * RS_SPLIT);
+#pragma unroll
+    for (int o = RS_SPLIT / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(gmask, cnt, o);
+    if (sub != 0) return;
     const unsigned long long packed = ((unsigned long long)(uint32_t)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)hyp);
     atomicMax(p.best + b, packed);
 }
@@ -422,7 +429,7 @@ extern "C" int gfb_homography_f32(const float* matches, const float* weights, in
         init_best_kernel<<<(B + 127) / 128, 128, 0, st>>>(p.best, B);
         cudaError_t e = cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        dim3 grid((n_hyp + RS_THREADS - 1) / RS_THREADS, B);
+        dim3 grid((n_hyp * RS_SPLIT + RS_THREADS - 1) / RS_THREADS, B);
         ransac_kernel<<<grid, RS_THREADS, smem, st>>>(p);
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;

@@ -71,7 +71,7 @@ __device__ __forceinline__ PointGeom point_geom(const LcParams& p, int b, int gy
 
 // debug counters (gfb_debug_local_corr_v2_counters): [0] lc_pt points on the global-memory path, [1] lc_tc2 points on
 // the gather path, [2] lc_tc2 gather tiles
-__device__ unsigned long long g_v2_stats[4];
+__device__ unsigned long long g_v2_stats[8];   // [4..7] (debug bit 0): epilogue warp 0 clocks waiting / TMEM pull / rows, chunks
 
 // =====================================================================================================================
 // lc_pt_kernel: one point per thread, the (2r+2)^2 patch in registers
@@ -326,8 +326,9 @@ struct TcCfg {
 
 constexpr int NMAX = 128;            // positions per B stage = TMEM columns per accumulator
 constexpr int NACC = 2;              // accumulators per CTA (256 TMEM columns; two CTAs share an SM)
-// warps [0, 4*NSPLIT): epilogue (warp w reads TMEM lanes 32*(w%4).., and owns output columns half w/4 of NSPLIT),
-// then one TMA producer warp and one MMA issuer warp
+constexpr int EPI_WARPS = 4;         // warp w reads TMEM lanes 32 w .. 32 w + 31
+constexpr int TMA_WARP = 4, MMA_WARP = 5;
+constexpr int TC_THREADS = 6 * 32;
 constexpr int LDW = 32;              // TMEM columns an epilogue warp pulls per image row
 constexpr int RPS = 2;               // image rows per B stage / accumulator (N = RPS * bw <= 128)
 
@@ -390,6 +391,11 @@ __device__ __forceinline__ uint32_t bf16x2_rn(float upper, float lower) {
     return d;
 }
 
+__device__ __forceinline__ void st_global_256(uint32_t* ptr, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
 // ---- pre-pass + plan (one launch) ------------------------------------------------------------------------------
 // 16 channels of one position: fp32 NCHW -> [bf16 hi(C) | bf16 lo(C)] position-major
 template <int C>
@@ -415,12 +421,9 @@ __device__ __forceinline__ void prep_unit(const float* __restrict__ x, uint32_t*
         lo[e] = bf16x2_rn(v[2 * e + 1] - h1, v[2 * e] - h0);
     }
     uint32_t* row = ws + (b * npos + pos) * C;          // 2C bf16 = C words per position
-    uint4* ph = reinterpret_cast<uint4*>(row + g * 8);
-    uint4* pl = reinterpret_cast<uint4*>(row + C / 2 + g * 8);
-    ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    // one 256-bit store per 32-byte piece: a 16-byte store would still move a whole 32-byte sector to L2
+    st_global_256(row + g * 8, hi);
+    st_global_256(row + C / 2 + g * 8, lo);
 }
 
 // blocks [0, nplan): bounding box of the windows of two tiles each (128 threads per tile); the other blocks convert
@@ -481,13 +484,14 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
     while (!mbar_try_wait(bar, parity)) __nanosleep(32);
 }
 __device__ __forceinline__ void st_stream_pred(float* ptr, float v, bool pred) {
+    // no "memory" clobber: the outputs are never read back, and the compiler must stay free to hoist the staging reads
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.f32 [%0], %1;\n\t}"
-                 ::"l"(ptr), "f"(v), "r"((int)pred) : "memory");
+                 ::"l"(ptr), "f"(v), "r"((int)pred));
 }
 
 // ---- main kernel ---------------------------------------------------------------------------------------------------
-template <int R, int C, int NSPLIT>
-__global__ void __launch_bounds__((4 * NSPLIT + 2) * 32, 2)
+template <int R, int C>
+__global__ void __launch_bounds__(TC_THREADS, 2)
 lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan,
               const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB) {
     constexpr int W = 2 * R + 2, KW = 2 * R + 1, KK = KW * KW;
@@ -495,8 +499,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
     constexpr int NKS = C / 16;                              // K = 16 steps per part
     constexpr uint32_t A_ATOM = 128 * 128, B_ATOM = NMAX * 128;
     constexpr uint32_t A_STAGE = ATOMS * A_ATOM, B_STAGE = ATOMS * B_ATOM;
-    constexpr int EPI_WARPS = 4 * NSPLIT, TMA_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
-    constexpr int KH = (KW + NSPLIT - 1) / NSPLIT;           // output columns per epilogue warp
+    constexpr int KH = KW;
     static_assert(W <= LDW, "window wider than the TMEM pull");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_base = smem;
@@ -622,14 +625,16 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
         // ================= epilogue warps: TMEM lane = lattice point =================
         // staging: column v of the pull goes to stg[v * 32] -- a lane-private column of a [LDW][32] block, so both the
         // 32 stores and the reads at the lane's own offset are bank-conflict free
-        const int quad = warp & 3, half = warp >> 2;
-        const int i0 = half * KH, i1 = min(KW, i0 + KH);          // this warp's output columns [i0, i1)
+        const int quad = warp;
+        constexpr int i0 = 0, i1 = KW;
         float* stg = ebuf + (size_t)warp * LDW * 32 + lane;
         auto stage = [&](const uint32_t (&r)[32]) {
 #pragma unroll
             for (int v = 0; v < 32; ++v) stg[v * 32] = __uint_as_float(r[v]);
         };
         uint32_t q = 0;
+        long long dbg_wait = 0, dbg_pull = 0, dbg_rows = 0, dbg_n = 0;
+        const bool dbg = p.debug & 1;
         for (int tile = blockIdx.x; tile < c.ntiles; tile += gridDim.x) {
             const TileDesc d = plan[tile];
             int t = tile;
@@ -642,19 +647,19 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
             float* outp = p.out + ((size_t)b * p.k_total + p.k_offset) * gg + (size_t)gy * G + gx;
             if (d.flags & TF_GATHER) {
                 if (valid)
-                    for (int k = half; k < KK; k += NSPLIT) st_stream(outp + (size_t)k * gg, lc_generic_point(p, b, k, gy, gx));
+                    for (int k = 0; k < KK; ++k) st_stream(outp + (size_t)k * gg, lc_generic_point(p, b, k, gy, gx));
                 continue;
             }
             const PointGeom pg = point_geom(p, b, gy, gx, valid, R);
             bool live = pg.live;
             if (valid && !live)
-                for (int k = half; k < KK; k += NSPLIT) st_stream(outp + (size_t)k * gg, 0.f);
+                for (int k = 0; k < KK; ++k) st_stream(outp + (size_t)k * gg, 0.f);
             if (d.flags & TF_EMPTY) continue;
             const int start = min(max(d.wx[quad] - d.x0, 0), c.bw - LDW);
             const int off = pg.xb - d.x0 - start;
             if (live && (off < 0 || off + W > LDW)) {      // window outside the warp's TMEM pull: exact gather
-                if (half == 0) atomicAdd(&g_v2_stats[1], 1ull);
-                for (int k = half; k < KK; k += NSPLIT) st_stream(outp + (size_t)k * gg, lc_generic_point(p, b, k, gy, gx));
+                atomicAdd(&g_v2_stats[1], 1ull);
+                for (int k = 0; k < KK; ++k) st_stream(outp + (size_t)k * gg, lc_generic_point(p, b, k, gy, gx));
                 live = false;
             }
             const int col0 = (live ? off : 0) + i0;                // first staged column this warp reads
@@ -664,70 +669,101 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
             float hprev[KH];
 #pragma unroll
             for (int i = 0; i < KH; ++i) hprev[i] = 0.f;
-            // one image row of D (or zeros outside the image): x-lerp, y-lerp with the previous row, predicated stores
-            auto emit_row = [&](int j, const float (&D)[KH + 1], bool act) {
+            const unsigned gg32 = (unsigned)gg;
+            // one image row of D, read back from the staging column at the lane's own offset: x-lerp, y-lerp with the
+            // previous row, predicated stores.  (Rolling reads: a D[] array next to the two 32-register TMEM pulls spills.)
+            auto emit_row = [&](int j, bool act) {
+                float* op = outp + ((ptrdiff_t)(j - 1) * KW + i0) * (ptrdiff_t)gg;
+                const bool st = act && j >= 1;
+                float d0 = stg[min(col0, LDW - 1) * 32];
+#pragma unroll
+                for (int i = 0; i < KH; ++i) {
+                    const float d1 = stg[min(col0 + i + 1, LDW - 1) * 32];
+                    const float h = a0 * d0 + a1 * d1;
+                    st_stream_pred(op + (size_t)((unsigned)i * gg32), wy0 * hprev[i] + wy1 * h, st && i0 + i < i1);
+                    hprev[i] = h;
+                    d0 = d1;
+                }
+            };
+            // a row outside the image: D = 0
+            auto emit_zero = [&](int j, bool act) {
                 float* op = outp + ((ptrdiff_t)(j - 1) * KW + i0) * (ptrdiff_t)gg;
                 const bool st = act && j >= 1;
 #pragma unroll
                 for (int i = 0; i < KH; ++i) {
-                    const float h = a0 * D[i] + a1 * D[i + 1];
-                    st_stream_pred(op + (size_t)i * gg, wy0 * hprev[i] + wy1 * h, st && i0 + i < i1);
-                    hprev[i] = h;
+                    st_stream_pred(op + (size_t)((unsigned)i * gg32), wy0 * hprev[i], st && i0 + i < i1);
+                    hprev[i] = 0.f;
                 }
             };
-            auto read_row = [&](float (&D)[KH + 1]) {
-#pragma unroll
-                for (int i = 0; i <= KH; ++i) D[i] = stg[min(col0 + i, LDW - 1) * 32];
-            };
-            float Z[KH + 1];
-#pragma unroll
-            for (int i = 0; i <= KH; ++i) Z[i] = 0.f;
             for (int y = d.ylo; y < min(d.y0, d.yhi); ++y) {            // rows above the image
                 const int j = y - yb;
                 const bool act = live && (unsigned)j < (unsigned)W;
-                if (__any_sync(0xffffffffu, act)) emit_row(j, Z, act);
+                if (__any_sync(0xffffffffu, act)) emit_zero(j, act);
             }
+            // Software-pipelined pull: while the rows of chunk ch are interpolated and stored, the two TMEM loads of chunk
+            // ch + 1 are already in flight (their registers were freed by staging the current rows first), and the
+            // accumulator goes back to the MMA issuer as soon as they have landed.
             const int nchunks = (d.nrows + RPS - 1) / RPS;
-            for (int ch = 0; ch < nchunks; ++ch, ++q) {
+            const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)start;
+            uint32_t rA[32], rB[32];
+            bool actA, actB, anyA, anyB;
+            int jA;
+            auto activity = [&](int ch) {
+                jA = d.y0 + ch * RPS - yb;
+                actA = live && (unsigned)jA < (unsigned)W;
+                actB = live && (ch * RPS + 1 < d.nrows) && (unsigned)(jA + 1) < (unsigned)W;
+                anyA = __any_sync(0xffffffffu, actA);
+                anyB = __any_sync(0xffffffffu, actB);
+            };
+            auto release = [&](uint32_t acc) {
+                tmem_ld_wait();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[acc]);
+            };
+            {   // first chunk of the tile: nothing to overlap with
+                const long long c0 = dbg ? clock64() : 0;
                 const uint32_t acc = q % NACC;
                 mbar_wait(&d_full[acc], (q / NACC) & 1);
                 fence_after_sync();
-                const int jA = d.y0 + ch * RPS - yb, jB = jA + 1;
-                const bool rowB = ch * RPS + 1 < d.nrows;
-                const bool actA = live && (unsigned)jA < (unsigned)W;
-                const bool actB = live && rowB && (unsigned)jB < (unsigned)W;
-                const bool anyA = __any_sync(0xffffffffu, actA), anyB = __any_sync(0xffffffffu, actB);
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)NMAX + (uint32_t)start;
-                if constexpr (NSPLIT == 1) {
-                    // both rows out of TMEM first, then the accumulator goes back to the MMA issuer at once
-                    uint32_t rA[32], rB[32];
-                    if (anyA) tmem_ld32(taddr, rA);
-                    if (anyB) tmem_ld32(taddr + (uint32_t)c.bw, rB);
-                    tmem_ld_wait();
-                    fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&d_empty[acc]);
-                    float D[KH + 1];
-                    if (anyA) { stage(rA); read_row(D); emit_row(jA, D, actA); }
-                    if (anyB) { stage(rB); read_row(D); emit_row(jB, D, actB); }
-                } else {
-                    uint32_t r[32];
-                    float D[KH + 1];
-                    if (anyA) { tmem_ld32(taddr, r); tmem_ld_wait(); stage(r); }
-                    if (anyB) tmem_ld32(taddr + (uint32_t)c.bw, r);
-                    if (anyA) { read_row(D); emit_row(jA, D, actA); }
-                    tmem_ld_wait();
-                    fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&d_empty[acc]);
-                    if (anyB) { stage(r); read_row(D); emit_row(jB, D, actB); }
+                activity(0);
+                if (anyA) tmem_ld32(tlane + acc * (uint32_t)NMAX, rA);
+                if (anyB) tmem_ld32(tlane + acc * (uint32_t)NMAX + (uint32_t)c.bw, rB);
+                release(acc);
+                if (dbg) dbg_pull += clock64() - c0;
+            }
+            for (int ch = 0; ch < nchunks; ++ch, ++q) {
+                const long long c1 = dbg ? clock64() : 0;
+                const bool cA = actA, cB = actB, hA = anyA, hB = anyB;
+                const int cj = jA;
+                const bool more = ch + 1 < nchunks;
+                const uint32_t nacc = (q + 1) % NACC;
+                if (more) {
+                    mbar_wait(&d_full[nacc], ((q + 1) / NACC) & 1);
+                    fence_after_sync();
+                    activity(ch + 1);
                 }
+                const long long c2 = dbg ? clock64() : 0;
+                if (hA) stage(rA);
+                if (more && anyA) tmem_ld32(tlane + nacc * (uint32_t)NMAX, rA);
+                if (hA) emit_row(cj, cA);
+                if (hB) stage(rB);
+                if (more && anyB) tmem_ld32(tlane + nacc * (uint32_t)NMAX + (uint32_t)c.bw, rB);
+                if (hB) emit_row(cj + 1, cB);
+                if (more) release(nacc);
+                if (dbg) { const long long c3 = clock64(); dbg_wait += c2 - c1; dbg_rows += c3 - c2; ++dbg_n; }
             }
             for (int y = max(d.y0 + d.nrows, d.ylo); y < d.yhi; ++y) {   // rows below the image
                 const int j = y - yb;
                 const bool act = live && (unsigned)j < (unsigned)W;
-                if (__any_sync(0xffffffffu, act)) emit_row(j, Z, act);
+                if (__any_sync(0xffffffffu, act)) emit_zero(j, act);
             }
+        }
+        if (dbg && warp == 0 && lane == 0) {
+            atomicAdd(&g_v2_stats[4], (unsigned long long)dbg_wait);
+            atomicAdd(&g_v2_stats[5], (unsigned long long)dbg_pull);
+            atomicAdd(&g_v2_stats[6], (unsigned long long)dbg_rows);
+            atomicAdd(&g_v2_stats[7], (unsigned long long)dbg_n);
         }
     }
     fence_before_sync();
@@ -753,8 +789,9 @@ static void tc2_config(int G, int Ws, int r, TcCfg& c) {
 }
 
 static int tc2_group(int B, size_t per_elem, int group) {
-    // elements per group: keep the bf16 workspace of one group L2-resident (~64 MB), groups of equal size
-    int gb = group > 0 ? group : (int)max((size_t)1, (size_t)(64u << 20) / per_elem);
+    // elements per group (equal sizes): one launch pair for the whole batch measured fastest (fewer, longer persistent
+    // kernels; the workspace need not stay L2-resident), so the cap only bounds the workspace at 512 MB
+    int gb = group > 0 ? group : (int)max((size_t)1, (size_t)(512u << 20) / per_elem);
     gb = min(gb, B);
     const int ngroups = (B + gb - 1) / gb;
     return (B + ngroups - 1) / ngroups;
@@ -763,8 +800,6 @@ static int tc2_group(int B, size_t per_elem, int group) {
 template <int R, int C>
 static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size_t ws_bytes, int group) {
     constexpr int ATOMS = (2 * C * 2 + 127) / 128;
-    constexpr int NSPLIT = 1;                              // 2 = eight epilogue warps, output columns split (measured slower)
-    constexpr int EPI_WARPS = 4 * NSPLIT, TC_THREADS = (EPI_WARPS + 2) * 32;
     TcCfg c;
     tc2_config(p0.G, p0.Ws, R, c);
     const int G = p0.G;
@@ -787,7 +822,7 @@ static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size
 
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto kern = lc_tc2_kernel<R, C, NSPLIT>;
+    auto kern = lc_tc2_kernel<R, C>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
 
@@ -873,6 +908,8 @@ extern "C" int gfb_local_corr_pt_f32(const float* f0, const float* f1, const flo
         if (tune == 1 || (tune == 0 && s <= 1.2f)) return lcv2::launch_pt<2, 16, 16, 8, 64, 24, 2, 3>(p, st);
         if (tune == 2 || (tune == 0 && s <= 2.0f)) return lcv2::launch_pt<2, 16, 16, 8, 64, 32, 2, 3>(p, st);
         if (tune == 4) return lcv2::launch_pt<2, 16, 16, 8, 56, 32, 4, 2>(p, st);
+        if (tune == 5) return lcv2::launch_pt<2, 16, 8, 16, 40, 48, 2, 3>(p, st);    // warp = 4 lattice rows x 8 points
+        if (tune == 6) return lcv2::launch_pt<2, 16, 8, 16, 64, 48, 2, 3>(p, st);
         return lcv2::launch_pt<2, 16, 8, 8, 64, 40, 2, 3>(p, st);
     }
     if (r == 4 && C == 32) {
@@ -887,9 +924,9 @@ extern "C" int gfb_local_corr_pt_f32(const float* f0, const float* f1, const flo
 
 extern "C" int gfb_debug_local_corr_v2_counters(unsigned long long* host_out4, int reset) {
     cudaError_t e = cudaSuccess;
-    if (host_out4) e = cudaMemcpyFromSymbol(host_out4, lcv2::g_v2_stats, 4 * sizeof(unsigned long long));
+    if (host_out4) e = cudaMemcpyFromSymbol(host_out4, lcv2::g_v2_stats, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess && reset) {
-        unsigned long long z[4] = {0, 0, 0, 0};
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         e = cudaMemcpyToSymbol(lcv2::g_v2_stats, z, sizeof(z));
     }
     return e == cudaSuccess ? GFB_OK : (int)e;
@@ -921,6 +958,8 @@ extern "C" int gfb_local_corr_tc2_f32(const float* f0, const float* f1, const fl
     int rc = fill_params(p, f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset);
     if (rc != GFB_OK) return rc;
     GFB_CHECK_ARG(group >= 0);
+    p.debug = (group >> 8) & 1;                // profiling aid: per-phase clocks of epilogue warp 0 into the debug counters
+    group &= 255;
     cudaStream_t st = gfb_cu(stream);
 #define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, group);
     GFB_TC2_CASE(4, 32) GFB_TC2_CASE(6, 64) GFB_TC2_CASE(7, 64) GFB_TC2_CASE(3, 32) GFB_TC2_CASE(5, 64) GFB_TC2_CASE(4, 64)

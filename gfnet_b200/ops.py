@@ -90,7 +90,7 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
                     raise NotImplementedError("local_correlation: the TMA-fed tcgen05 kernel covers bilinear/zeros with "
                                               f"(r, C) in {sorted(_TC2_SHAPES)}, got r={r}, C={c}")
                 group = int(algo) >> 4 if base == ALGO_TC2 else 0
-                nws = int(lib.gfb_local_corr_tc2_workspace_bytes(B, c, hs, ws, G, r, group))
+                nws = int(lib.gfb_local_corr_tc2_workspace_bytes(B, c, hs, ws, G, r, group & 255))
                 wsbuf = torch.empty(nws, device=f0.device, dtype=torch.uint8)
                 rc = lib.gfb_local_corr_tc2_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r,
                                                 kk * num_level, kk * level, group, ptr(wsbuf), nws, st)
@@ -160,7 +160,7 @@ def _stream_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
 def local_correlation_v2_counters(reset=True):
     """(lc_pt points on the global-memory path, lc_tc2 points on the gather path, lc_tc2 gather tiles, 0); synchronises."""
     import ctypes
-    buf = (ctypes.c_ulonglong * 4)()
+    buf = (ctypes.c_ulonglong * 8)()
     check(lib.gfb_debug_local_corr_v2_counters(buf, int(reset)), "counters")
     return tuple(int(v) for v in buf)
 

@@ -95,9 +95,10 @@ int gfb_local_corr_pt_f32(const float* f0, const float* f1, const float* flow, f
 size_t gfb_local_corr_tc2_workspace_bytes(int B, int C, int Hs, int Ws, int G, int r, int group);
 /* how many (pre-pass, main) launch pairs one gfb_local_corr_tc2_f32 call issues for these shapes */
 int gfb_local_corr_tc2_groups(int B, int C, int Hs, int Ws, int G, int group);
-/* Debug aid (synchronises): host_out4 = {lc_pt points on the global-memory path, lc_tc2 points on the gather path,
- * lc_tc2 gather tiles, 0}; reset != 0 zeroes. */
-int gfb_debug_local_corr_v2_counters(unsigned long long* host_out4, int reset);
+/* Debug aid (synchronises): host_out8 = {lc_pt points on the global-memory path, lc_tc2 points on the gather path,
+ * lc_tc2 gather tiles, 0, and -- when the tc2 call had bit 8 of `group` set -- SM clocks epilogue warp 0 of every CTA
+ * spent waiting for an accumulator / pulling it out of TMEM / emitting rows, and the chunk count}; reset != 0 zeroes. */
+int gfb_debug_local_corr_v2_counters(unsigned long long* host_out8, int reset);
 int gfb_local_corr_tc2_f32(const float* f0, const float* f1, const float* flow, float* out,
                            int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                            int k_total, int k_offset, int group,

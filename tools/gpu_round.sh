@@ -10,6 +10,7 @@ tail -22 gpurun_out/kbench.log | cut -c1-200
 timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.json
 if [ -n "$REF_ARM" ]; then timeout 600 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -1 gpurun_out/bench_ref.json; fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/launches.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:kde4 -o gpurun_out/kde_sym -f python tools/profile_kde.py --pairs 32 --algo 2 > gpurun_out/ncu_kde.log 2>&1
 for sc in ${NCU_SCALES:-4 2}; do
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:lc_ -c 3 -o gpurun_out/lc_v2_s$sc -f python tools/profile_lc.py --scale $sc --algo 0 > gpurun_out/ncu_s$sc.log 2>&1
 done
