@@ -56,7 +56,7 @@ def _load():
     lib.gfb_kde_f32.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp]
     lib.gfb_kde_sym_workspace_bytes.restype = sz
     lib.gfb_kde_sym_workspace_bytes.argtypes = [i32, i32]
-    lib.gfb_kde_sym_f32.argtypes = [vp, vp, i32, i32, f32, vp, sz, vp]
+    lib.gfb_kde_sym_f32.argtypes = [vp, vp, i32, i32, f32, f32, vp, sz, vp]
     lib.gfb_match_postprocess_f32.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.gfb_sample_keys_f32.argtypes = [vp, vp, vp, i64, f32, vp]
     lib.gfb_balance_keys_f32.argtypes = [vp, vp, vp, i64, f32, vp]

@@ -138,17 +138,43 @@ constexpr float KS_FIX = 1099511627776.f;   // 2^40
 
 __device__ __forceinline__ unsigned long long kde_fix(float v) { return __float2ull_rn(v * KS_FIX); }
 
+// Optional cut-off (cut2 > 0): the points arrive sorted along a Morton curve, bb holds the bounding box of every
+// 128-point block, and a tile pair whose boxes are further apart than the cut-off radius is skipped -- each of its
+// terms is below exp(-cut_sigmas^2 / 2) (2.3e-11 at 7 sigma, far below one fp32 ulp of a density that is >= 1).
+__device__ __forceinline__ float bb_dist2(const float* __restrict__ a, const float* __restrict__ b) {
+    float d2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const float g = fmaxf(0.f, fmaxf(a[d] - b[4 + d], b[d] - a[4 + d]));     // [0..3] = lo, [4..7] = hi
+        d2 = fmaf(g, g, d2);
+    }
+    return d2;
+}
+
 __global__ void __launch_bounds__(256, 3) kde4_sym_kernel(const float* __restrict__ x, unsigned long long* __restrict__ acc64,
-                                                          int M, int nb, float scale) {
+                                                          int M, int nb, float scale, const float* __restrict__ bb, float cut2) {
     // column block, 8 points per tj at a pitch of 9: the two half-warps of a warp (tj, tj + 1) read different banks
     __shared__ float4 sy[2][KS_PITCH];          // 2 * y'
     __shared__ float sn[2][KS_PITCH];           // -|y'|^2
     __shared__ float srow[16][KS_T];            // end of the CTA: row sums of the 16 column groups
+    __shared__ int jl[KS_JC + 1];               // column blocks of this CTA that survive the cut-off, then their count
     const int I = blockIdx.x, b = blockIdx.z;
-    const int j0 = I + blockIdx.y * KS_JC;
-    if (j0 >= nb) return;
-    const int j1 = min(j0 + KS_JC, nb);
+    const int jfirst = I + blockIdx.y * KS_JC;
+    if (jfirst >= nb) return;
     const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
+    if (tid < 32) {
+        const int J = jfirst + tid;
+        bool keep = tid < KS_JC && J < nb;
+        if (keep && cut2 > 0.f && J != I)
+            keep = bb_dist2(bb + ((size_t)b * nb + I) * 8, bb + ((size_t)b * nb + J) * 8) <= cut2;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) jl[__popc(m & ((1u << tid) - 1u))] = J;
+        if (tid == 0) jl[KS_JC] = __popc(m);
+    }
+    __syncthreads();
+    const int nj = jl[KS_JC];
+    if (nj == 0) return;
+    const int j0 = jl[0];
     const float4* xb = reinterpret_cast<const float4*>(x) + (size_t)b * M;
 
     unsigned long long x2[4][4], nn2[4], rs2[4];
@@ -182,11 +208,12 @@ __global__ void __launch_bounds__(256, 3) kde4_sym_kernel(const float* __restric
         put(0, tid, idx, idx < M ? __ldg(xb + idx) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
     __syncthreads();
-    for (int J = j0; J < j1; ++J) {
-        const int buf = (J - j0) & 1;
+    for (int k = 0; k < nj; ++k) {
+        const int J = jl[k];
+        const int buf = k & 1;
         // the upper half of the CTA fetches the next column block while everybody computes on this one
-        const bool pf = tid >= KS_T && J + 1 < j1;
-        const int pidx = (J + 1) * KS_T + tid - KS_T;
+        const bool pf = tid >= KS_T && k + 1 < nj;
+        const int pidx = (pf ? jl[k + 1] : 0) * KS_T + tid - KS_T;
         float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (pf && pidx < M) pv = __ldg(xb + pidx);
         unsigned long long cs2[8];
@@ -260,9 +287,60 @@ __global__ void __launch_bounds__(256, 3) kde4_sym_kernel(const float* __restric
     }
 }
 
-__global__ void __launch_bounds__(256) kde_finish_kernel(const unsigned long long* __restrict__ acc64, float* __restrict__ density, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        density[i] = (float)((double)acc64[i] * (1.0 / 1099511627776.0));
+// density[b, perm[i]] = accumulated fixed-point sum of sorted point i (perm == nullptr: identity)
+__global__ void __launch_bounds__(256) kde_finish_kernel(const unsigned long long* __restrict__ acc64, const long long* __restrict__ perm,
+                                                         float* __restrict__ density, int M, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = (float)((double)acc64[i] * (1.0 / 1099511627776.0));
+        density[perm ? (i / M) * M + (size_t)perm[i] : i] = v;
+    }
+}
+
+// Morton code (10 + 10 bits) of the first two coordinates as an exactly representable float sort key
+__global__ void __launch_bounds__(256) kde_keys_kernel(const float4* __restrict__ x, float* __restrict__ keys, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x + i);
+        uint32_t qx = (uint32_t)fminf(fmaxf((v.x + 1.f) * 511.5f, 0.f), 1023.f);
+        uint32_t qy = (uint32_t)fminf(fmaxf((v.y + 1.f) * 511.5f, 0.f), 1023.f);
+        auto spread = [](uint32_t a) {
+            a = (a | (a << 8)) & 0x00FF00FFu; a = (a | (a << 4)) & 0x0F0F0F0Fu;
+            a = (a | (a << 2)) & 0x33333333u; a = (a | (a << 1)) & 0x55555555u;
+            return a;
+        };
+        keys[i] = (float)(spread(qx) | (spread(qy) << 1));
+    }
+}
+
+// xs[b, i] = x[b, perm[b, i]] and the bounding box of every block of 128 sorted points (one CTA per block)
+__global__ void __launch_bounds__(KS_T) kde_gather_bbox_kernel(const float4* __restrict__ x, const long long* __restrict__ perm,
+                                                               float4* __restrict__ xs, float* __restrict__ bb, int M, int nb) {
+    __shared__ float sm[4][8];
+    const int blk = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+    const int i = blk * KS_T + t;
+    float lo[4], hi[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) { lo[d] = 3.0e38f; hi[d] = -3.0e38f; }
+    if (i < M) {
+        const float4 v = __ldg(x + (size_t)b * M + (size_t)perm[(size_t)b * M + i]);
+        xs[(size_t)b * M + i] = v;
+        lo[0] = hi[0] = v.x; lo[1] = hi[1] = v.y; lo[2] = hi[2] = v.z; lo[3] = hi[3] = v.w;
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+    if ((t & 31) == 0)
+#pragma unroll
+        for (int d = 0; d < 4; ++d) { sm[t >> 5][d] = lo[d]; sm[t >> 5][4 + d] = hi[d]; }
+    __syncthreads();
+    if (t < 8) {
+        float v = sm[0][t];
+        for (int w = 1; w < 4; ++w) v = t < 4 ? fminf(v, sm[w][t]) : fmaxf(v, sm[w][t]);
+        bb[((size_t)b * nb + blk) * 8 + t] = v;
+    }
 }
 
 // Any D <= 8 (not on the GFNet path; kept so the op is a full drop-in for kde(x) with other widths).
@@ -287,29 +365,54 @@ __global__ void __launch_bounds__(KDE_THREADS) kde_generic_kernel(const float* _
 
 using namespace gfb;
 
+extern "C" size_t gfb_topk_workspace_bytes(int B, long long n, int k);
+extern "C" int gfb_topk_desc_f32(const float* keys, int64_t* idx_out, int B, long long n, int k,
+                                 void* workspace, size_t workspace_bytes, gfb_stream_t stream);
+
+static inline size_t kde_align(size_t v) { return (v + 255) / 256 * 256; }
+
 extern "C" size_t gfb_kde_sym_workspace_bytes(int B, int M) {
-    return B > 0 && M > 0 ? (size_t)B * M * sizeof(unsigned long long) : 0;
+    if (B <= 0 || M <= 0) return 0;
+    const size_t n = (size_t)B * M, nb = (size_t)(M + KS_T - 1) / KS_T;
+    // fixed-point sums | sort keys | permutation | sorted points | block boxes | top-k scratch
+    return kde_align(n * 8) + kde_align(n * 4) + kde_align(n * 8) + kde_align(n * 16) + kde_align((size_t)B * nb * 32) +
+           kde_align(gfb_topk_workspace_bytes(B, M, M));
 }
 
-// kde(x) with y = x (down == 1), D = 4: symmetric evaluation, see kde4_sym_kernel.
-extern "C" int gfb_kde_sym_f32(const float* x, float* density, int B, int M, float std,
+// kde(x) with y = x (down == 1), D = 4: symmetric evaluation, see kde4_sym_kernel.  cut_sigmas > 0 additionally sorts
+// the points along a Morton curve and skips tile pairs further apart than cut_sigmas * std (0 = evaluate every pair).
+extern "C" int gfb_kde_sym_f32(const float* x, float* density, int B, int M, float std, float cut_sigmas,
                                void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
-    GFB_CHECK_ARG(x && density && B > 0 && M > 0 && std > 0.f);
+    GFB_CHECK_ARG(x && density && B > 0 && M > 0 && std > 0.f && cut_sigmas >= 0.f);
     GFB_CHECK_ARG(B <= 65535);
-    if (!gfb_aligned(x, 16) || !gfb_aligned(workspace, 8)) return GFB_EALIGN;
-    const size_t need = (size_t)B * M * sizeof(unsigned long long);
-    if (!workspace || workspace_bytes < need) return GFB_EWORKSPACE;
+    if (!gfb_aligned(x, 16) || !gfb_aligned(workspace, 256)) return GFB_EALIGN;
+    if (!workspace || workspace_bytes < gfb_kde_sym_workspace_bytes(B, M)) return GFB_EWORKSPACE;
     const float scale = (float)sqrt(1.4426950408889634 / (2.0 * (double)std * (double)std));
     cudaStream_t st = gfb_cu(stream);
-    cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
-    if (e != cudaSuccess) return (int)e;
     const int nb = (M + KS_T - 1) / KS_T;
     if (nb > 65535) return GFB_EUNSUPPORTED;
-    dim3 grid((unsigned)nb, (unsigned)((nb + KS_JC - 1) / KS_JC), (unsigned)B);
-    unsigned long long* acc = reinterpret_cast<unsigned long long*>(workspace);
-    kde4_sym_kernel<<<grid, 256, 0, st>>>(x, acc, M, nb, scale);
     const size_t n = (size_t)B * M;
-    kde_finish_kernel<<<(unsigned)min((size_t)148 * 8, (n + 255) / 256), 256, 0, st>>>(acc, density, n);
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(w); w += kde_align(n * 8);
+    float* keys = reinterpret_cast<float*>(w); w += kde_align(n * 4);
+    long long* perm = reinterpret_cast<long long*>(w); w += kde_align(n * 8);
+    float4* xs = reinterpret_cast<float4*>(w); w += kde_align(n * 16);
+    float* bb = reinterpret_cast<float*>(w); w += kde_align((size_t)B * nb * 32);
+    cudaError_t e = cudaMemsetAsync(acc, 0, n * 8, st);
+    if (e != cudaSuccess) return (int)e;
+    // the sort reuses the top-k kernel (k = n): it orders at most 20480 keys per row
+    const bool cut = cut_sigmas > 0.f && gfb_topk_workspace_bytes(B, M, M) > 0 && M <= 20480 && nb > KS_JC;
+    const unsigned gs = (unsigned)min((size_t)148 * 8, (n + 255) / 256);
+    if (cut) {
+        kde_keys_kernel<<<gs, 256, 0, st>>>(reinterpret_cast<const float4*>(x), keys, n);
+        int rc = gfb_topk_desc_f32(keys, reinterpret_cast<int64_t*>(perm), B, M, M, w, gfb_topk_workspace_bytes(B, M, M), stream);
+        if (rc != GFB_OK) return rc;
+        kde_gather_bbox_kernel<<<dim3((unsigned)nb, (unsigned)B), KS_T, 0, st>>>(reinterpret_cast<const float4*>(x), perm, xs, bb, M, nb);
+    }
+    dim3 grid((unsigned)nb, (unsigned)((nb + KS_JC - 1) / KS_JC), (unsigned)B);
+    const float r = cut_sigmas * std;
+    kde4_sym_kernel<<<grid, 256, 0, st>>>(cut ? reinterpret_cast<const float*>(xs) : x, acc, M, nb, scale, bb, cut ? r * r : 0.f);
+    kde_finish_kernel<<<gs, 256, 0, st>>>(acc, cut ? perm : nullptr, density, M, n);
     GFB_LAUNCH_RESULT();
 }
 

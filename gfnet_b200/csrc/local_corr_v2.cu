@@ -312,15 +312,21 @@ struct TileDesc {
     int ylo, yhi;    // unclipped row range of the union of the windows
     int flags;
     int wx[4];       // per epilogue warp: smallest window origin of its 32 points
-    int pad[2];
+    int bwi;         // staged row width of this tile = NBW_FIRST + 8 * bwi positions (index of the TMA box)
+    int pad;
 };
 enum { TF_EMPTY = 1, TF_GATHER = 2 };
+
+// The main kernel is bound by L2 -> shared-memory traffic of the haloed B tiles, so every tile streams the narrowest box
+// that holds its windows: one tensor map per width 32, 40, ..., 64.
+constexpr int NBW = 5, NBW_FIRST = 32;
+struct TmapSet { CUtensorMap m[NBW]; };
 
 struct TcCfg {
     int blx, bly;            // lattice points per warp block (blx * bly = 32)
     int nbx, nby;            // warp blocks per tile (nbx * nby = 4)
     int tiles_x, tiles_y, ntiles;
-    int bw, rps;             // staged row width (multiple of 16, >= 32), image rows per B stage (N = bw * rps <= 128)
+    int bw, rps;             // widest staged row (64), image rows per B stage (N = bw * rps <= 128)
     int nstb;
 };
 
@@ -463,7 +469,7 @@ __global__ void __launch_bounds__(256) lc_prep_plan_kernel(const LcParams p, con
             X0 = min(X0, sm[half][w][0]); X1 = max(X1, sm[half][w][1]);
             Y0 = min(Y0, sm[half][w][2]); Y1 = max(Y1, sm[half][w][3]);
         }
-        d.x0 = 0; d.y0 = 0; d.nrows = 0; d.ylo = 0; d.yhi = 0; d.flags = 0; d.pad[0] = 0; d.pad[1] = 0;
+        d.x0 = 0; d.y0 = 0; d.nrows = 0; d.ylo = 0; d.yhi = 0; d.flags = 0; d.bwi = 0; d.pad = 0;
         for (int w = 0; w < 4; ++w) d.wx[w] = 0;
         if (X0 == INT_MAX) {
             d.flags = TF_EMPTY;
@@ -473,6 +479,7 @@ __global__ void __launch_bounds__(256) lc_prep_plan_kernel(const LcParams p, con
             d.nrows = min(Y1, p.Hs) - d.y0;
             d.ylo = Y0; d.yhi = Y1;
             for (int w = 0; w < 4; ++w) d.wx[w] = sm[half][w][0] == INT_MAX ? X0 : sm[half][w][0];
+            d.bwi = min(max((X1 - X0 - NBW_FIRST + 7) / 8, 0), NBW - 1);
             if (X1 - X0 > c.bw) { d.flags = TF_GATHER; atomicAdd(&g_v2_stats[2], 1ull); }
         }
         plan[tile] = d;
@@ -493,13 +500,12 @@ __device__ __forceinline__ void st_stream_pred(float* ptr, float v, bool pred) {
 template <int R, int C>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan,
-              const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB) {
+              const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ TmapSet tmapB) {
     constexpr int W = 2 * R + 2, KW = 2 * R + 1, KK = KW * KW;
     constexpr int ATOMS = (2 * C * 2 + 127) / 128;          // 128-byte atoms per K-major row [hi(C) | lo(C)] of bf16
     constexpr int NKS = C / 16;                              // K = 16 steps per part
     constexpr uint32_t A_ATOM = 128 * 128, B_ATOM = NMAX * 128;
     constexpr uint32_t A_STAGE = ATOMS * A_ATOM, B_STAGE = ATOMS * B_ATOM;
-    constexpr int KH = KW;
     static_assert(W <= LDW, "window wider than the TMEM pull");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_base = smem;
@@ -517,7 +523,6 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int G = p.G;
     const size_t gg = (size_t)G * G;
-    const int nchunk_cols = RPS * c.bw;
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();          // the swizzled operand stages need 1024-byte alignment
@@ -536,7 +541,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
         // ================= TMA producer =================
         if (lane == 0) {
             tma_prefetch_desc(&tmapA);
-            tma_prefetch_desc(&tmapB);
+            for (int k = 0; k < NBW; ++k) tma_prefetch_desc(&tmapB.m[k]);
             uint32_t q = 0, tt = 0;
             for (int tile = blockIdx.x; tile < c.ntiles; tile += gridDim.x) {
                 const TileDesc d = plan[tile];
@@ -546,6 +551,8 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                 const int ty = t % c.tiles_y;
                 const int b = t / c.tiles_y;
                 const int nchunks = (d.nrows + RPS - 1) / RPS;
+                const CUtensorMap* tmB = &tmapB.m[d.bwi];
+                const uint32_t b_bytes = (uint32_t)(ATOMS * RPS * (NBW_FIRST + 8 * d.bwi) * 128);
                 // the first B stages of this tile go out before its A tile: the A buffer is free only when the previous
                 // tile's last MMA has retired, the B ring usually has room earlier
                 const int pre = min(nchunks, c.nstb);
@@ -563,10 +570,10 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                     }
                     const uint32_t s = q % c.nstb;
                     mbar_wait_sleep(&b_empty[s], ((q / c.nstb) & 1) ^ 1);
-                    mbar_expect_tx(&b_full[s], (uint32_t)(ATOMS * nchunk_cols * 128));
+                    mbar_expect_tx(&b_full[s], b_bytes);
 #pragma unroll
                     for (int at = 0; at < ATOMS; ++at)
-                        tma_load_4d(b_base + (size_t)s * B_STAGE + at * B_ATOM, &tmapB, &b_full[s], at * 32, d.x0,
+                        tma_load_4d(b_base + (size_t)s * B_STAGE + at * B_ATOM, tmB, &b_full[s], at * 32, d.x0,
                                     d.y0 + ch * RPS, b);
                 }
                 if (pre == nchunks) {                  // short tile: every B stage went out first
@@ -587,13 +594,13 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t q = 0, tt = 0;
-            const uint32_t idesc = idesc_bf16(nchunk_cols);
             const uint32_t a_addr = smem_u32(a_base);
             for (int tile = blockIdx.x; tile < c.ntiles; tile += gridDim.x) {
                 const TileDesc d = plan[tile];
                 if (d.flags) continue;
                 mbar_wait_sleep(a_full, tt & 1);
                 const int nchunks = (d.nrows + RPS - 1) / RPS;
+                const uint32_t idesc = idesc_bf16(RPS * (NBW_FIRST + 8 * d.bwi));
                 for (int ch = 0; ch < nchunks; ++ch, ++q) {
                     const uint32_t s = q % c.nstb, acc = q % NACC;
                     mbar_wait_sleep(&b_full[s], (q / c.nstb) & 1);
@@ -626,9 +633,9 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
         // staging: column v of the pull goes to stg[v * 32] -- a lane-private column of a [LDW][32] block, so both the
         // 32 stores and the reads at the lane's own offset are bank-conflict free
         const int quad = warp;
-        constexpr int i0 = 0, i1 = KW;
         float* stg = ebuf + (size_t)warp * LDW * 32 + lane;
         auto stage = [&](const uint32_t (&r)[32]) {
+            if (p.debug & 4) { stg[0] = __uint_as_float(r[0] ^ r[31]); return; }
 #pragma unroll
             for (int v = 0; v < 32; ++v) stg[v * 32] = __uint_as_float(r[v]);
         };
@@ -655,43 +662,50 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
             if (valid && !live)
                 for (int k = 0; k < KK; ++k) st_stream(outp + (size_t)k * gg, 0.f);
             if (d.flags & TF_EMPTY) continue;
-            const int start = min(max(d.wx[quad] - d.x0, 0), c.bw - LDW);
+            const int tbw = NBW_FIRST + 8 * d.bwi;                 // this tile's staged row width
+            const int start = min(max(d.wx[quad] - d.x0, 0), tbw - LDW);
             const int off = pg.xb - d.x0 - start;
             if (live && (off < 0 || off + W > LDW)) {      // window outside the warp's TMEM pull: exact gather
                 atomicAdd(&g_v2_stats[1], 1ull);
                 for (int k = 0; k < KK; ++k) st_stream(outp + (size_t)k * gg, lc_generic_point(p, b, k, gy, gx));
                 live = false;
             }
-            const int col0 = (live ? off : 0) + i0;                // first staged column this warp reads
+            const int col0 = live ? off : 0;                       // first staged column this lane reads (col0 + KW <= LDW - 1)
             const float a1 = pg.fx, a0 = 1.f - pg.fx;
             const float wy1 = pg.fy * p.inv_sqrt_c, wy0 = (1.f - pg.fy) * p.inv_sqrt_c;
             const int yb = pg.yb;
-            float hprev[KH];
+            float hprev[KW];
 #pragma unroll
-            for (int i = 0; i < KH; ++i) hprev[i] = 0.f;
+            for (int i = 0; i < KW; ++i) hprev[i] = 0.f;
             const unsigned gg32 = (unsigned)gg;
-            // one image row of D, read back from the staging column at the lane's own offset: x-lerp, y-lerp with the
-            // previous row, predicated stores.  (Rolling reads: a D[] array next to the two 32-register TMEM pulls spills.)
+            // element index of this lane's first output; the launcher guarantees B * k_total * G * G < 2^31
+            const unsigned lane_idx = (((unsigned)b * (unsigned)p.k_total + (unsigned)p.k_offset) * (unsigned)G + (unsigned)gy) * (unsigned)G + (unsigned)gx;
+            // one image row of D, read back from the staging column at the lane's own offset (immediate offsets from
+            // rowp): x-lerp, y-lerp with the previous row, predicated streaming stores addressed as out[32-bit index]
+            // (a uniform base + one IMAD.WIDE per store instead of 64-bit pointer arithmetic per output)
+            const float* rowp = stg + col0 * 32;
             auto emit_row = [&](int j, bool act) {
-                float* op = outp + ((ptrdiff_t)(j - 1) * KW + i0) * (ptrdiff_t)gg;
-                const bool st = act && j >= 1;
-                float d0 = stg[min(col0, LDW - 1) * 32];
+                const bool st = act && j >= 1 && !(p.debug & 2);
+                unsigned idx = lane_idx + (unsigned)(j - 1) * (KW * gg32);
+                float d0 = rowp[0];
 #pragma unroll
-                for (int i = 0; i < KH; ++i) {
-                    const float d1 = stg[min(col0 + i + 1, LDW - 1) * 32];
+                for (int i = 0; i < KW; ++i) {
+                    const float d1 = rowp[(i + 1) * 32];
                     const float h = a0 * d0 + a1 * d1;
-                    st_stream_pred(op + (size_t)((unsigned)i * gg32), wy0 * hprev[i] + wy1 * h, st && i0 + i < i1);
+                    if (st) __stcs(p.out + idx, wy0 * hprev[i] + wy1 * h);
+                    idx += gg32;
                     hprev[i] = h;
                     d0 = d1;
                 }
             };
             // a row outside the image: D = 0
             auto emit_zero = [&](int j, bool act) {
-                float* op = outp + ((ptrdiff_t)(j - 1) * KW + i0) * (ptrdiff_t)gg;
                 const bool st = act && j >= 1;
+                unsigned idx = lane_idx + (unsigned)(j - 1) * (KW * gg32);
 #pragma unroll
-                for (int i = 0; i < KH; ++i) {
-                    st_stream_pred(op + (size_t)((unsigned)i * gg32), wy0 * hprev[i], st && i0 + i < i1);
+                for (int i = 0; i < KW; ++i) {
+                    if (st) __stcs(p.out + idx, wy0 * hprev[i]);
+                    idx += gg32;
                     hprev[i] = 0.f;
                 }
             };
@@ -728,7 +742,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                 fence_after_sync();
                 activity(0);
                 if (anyA) tmem_ld32(tlane + acc * (uint32_t)NMAX, rA);
-                if (anyB) tmem_ld32(tlane + acc * (uint32_t)NMAX + (uint32_t)c.bw, rB);
+                if (anyB) tmem_ld32(tlane + acc * (uint32_t)NMAX + (uint32_t)tbw, rB);
                 release(acc);
                 if (dbg) dbg_pull += clock64() - c0;
             }
@@ -748,7 +762,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                 if (more && anyA) tmem_ld32(tlane + nacc * (uint32_t)NMAX, rA);
                 if (hA) emit_row(cj, cA);
                 if (hB) stage(rB);
-                if (more && anyB) tmem_ld32(tlane + nacc * (uint32_t)NMAX + (uint32_t)c.bw, rB);
+                if (more && anyB) tmem_ld32(tlane + nacc * (uint32_t)NMAX + (uint32_t)tbw, rB);
                 if (hB) emit_row(cj + 1, cB);
                 if (more) release(nacc);
                 if (dbg) { const long long c3 = clock64(); dbg_wait += c2 - c1; dbg_rows += c3 - c2; ++dbg_n; }
@@ -783,8 +797,8 @@ static void tc2_config(int G, int Ws, int r, TcCfg& c) {
     const int tw = c.nbx * c.blx, th = c.nby * c.bly;
     c.tiles_x = (G + tw - 1) / tw;
     c.tiles_y = (G + th - 1) / th;
-    int bw = ((int)ceilf((float)tw * s * 1.35f) + W + 2 + 15) & ~15;
-    c.bw = min(max(bw, LDW), NMAX / RPS);                  // a B stage = RPS image rows of bw positions
+    (void)s;
+    c.bw = NMAX / RPS;                                     // widest box; tiles whose windows spread further take the gather path
     c.rps = RPS;
 }
 
@@ -808,6 +822,7 @@ static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size
     const size_t budget = 112 * 1024 + 256;                // two CTAs per SM
     c.nstb = (int)min((size_t)6, (budget - fixed) / b_stage);
     if (c.nstb < 2) return GFB_EUNSUPPORTED;
+    if ((size_t)p0.B * p0.k_total * G * G >= (1ull << 31)) return GFB_EUNSUPPORTED;     // 32-bit output indices
     const size_t smem = fixed + c.nstb * b_stage;
 
     const size_t ws0_per = (size_t)G * G * C * 4, ws1_per = (size_t)p0.Hs * p0.Ws * C * 4;
@@ -843,7 +858,8 @@ static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
 
-        CUtensorMap tmapA, tmapB;
+        CUtensorMap tmapA;
+        TmapSet tmapB;
         {
             uint64_t dims[4] = {(uint64_t)C, (uint64_t)G, (uint64_t)G, (uint64_t)p.B};
             uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)G * C * 4, (uint64_t)gg * C * 4};
@@ -851,11 +867,11 @@ static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size
             int rc = gfb_encode_tmap_f32(&tmapA, ws0, 4, dims, strides, box, 3);
             if (rc != GFB_OK) return rc;
         }
-        {
+        for (int k = 0; k < NBW; ++k) {
             uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B};
             uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)p.Ws * C * 4, (uint64_t)p.Hs * p.Ws * C * 4};
-            uint32_t box[4] = {32u, (uint32_t)c.bw, (uint32_t)RPS, 1u};
-            int rc = gfb_encode_tmap_f32(&tmapB, ws1, 4, dims, strides, box, 3);
+            uint32_t box[4] = {32u, (uint32_t)(NBW_FIRST + 8 * k), (uint32_t)RPS, 1u};
+            int rc = gfb_encode_tmap_f32(&tmapB.m[k], ws1, 4, dims, strides, box, 3);
             if (rc != GFB_OK) return rc;
         }
         kern<<<min(c.ntiles, 2 * sms), TC_THREADS, smem, st>>>(p, c, plan, tmapA, tmapB);
@@ -958,7 +974,8 @@ extern "C" int gfb_local_corr_tc2_f32(const float* f0, const float* f1, const fl
     int rc = fill_params(p, f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset);
     if (rc != GFB_OK) return rc;
     GFB_CHECK_ARG(group >= 0);
-    p.debug = (group >> 8) & 1;                // profiling aid: per-phase clocks of epilogue warp 0 into the debug counters
+    p.debug = (group >> 8) & 7;                // profiling aids: bit 0 per-phase clocks of epilogue warp 0 into the debug counters,
+                                               // bit 1 suppress the output stores, bit 2 skip the staging stores (results are wrong)
     group &= 255;
     cudaStream_t st = gfb_cu(stream);
 #define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, group);

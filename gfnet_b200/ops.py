@@ -174,9 +174,10 @@ def local_correlation_counters(reset=True):
 
 
 KDE_AUTO, KDE_FULL, KDE_SYMMETRIC = 0, 1, 2
+KDE_CUT_SIGMAS = 7.0     # symmetric kernel: tile pairs further apart than 7 std are skipped (terms < 2.3e-11); 0 = none
 
 
-def kde(x, std=0.1, half=True, down=None, *, algo=KDE_AUTO):
+def kde(x, std=0.1, half=True, down=None, *, algo=KDE_AUTO, cut_sigmas=None):
     """Gaussian kernel density of the rows of ``x [M,D]`` (or batched ``[B,M,D]``).
 
     reference: utils/kde.py:4-13.  Arithmetic is fp32 (the parity target is the reference's
@@ -201,7 +202,8 @@ def kde(x, std=0.1, half=True, down=None, *, algo=KDE_AUTO):
         if algo == KDE_SYMMETRIC or (algo == KDE_AUTO and sym_ok and M >= 2048):
             nws = int(lib.gfb_kde_sym_workspace_bytes(B, M))
             wsbuf = torch.empty(nws, device=xb.device, dtype=torch.uint8)
-            rc = lib.gfb_kde_sym_f32(ptr(xb), ptr(dens), B, M, float(std), ptr(wsbuf), nws, stream_ptr(xb.device))
+            cs = KDE_CUT_SIGMAS if cut_sigmas is None else float(cut_sigmas)
+            rc = lib.gfb_kde_sym_f32(ptr(xb), ptr(dens), B, M, float(std), cs, ptr(wsbuf), nws, stream_ptr(xb.device))
         else:
             rc = lib.gfb_kde_f32(ptr(xb), ptr(dens), B, M, D, dn, float(std), stream_ptr(xb.device))
     check(rc, "kde")

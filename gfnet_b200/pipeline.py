@@ -31,7 +31,7 @@ class HotPath:
             for sc in p:
                 b = sc["f1"].shape[0]
                 n += len(sc["flows"]) * ops.local_correlation_launches(b, sc["c"], sc["hs"], sc["hs"], sc["G"], sc["r"])
-        n += 1 + 1 + 1 + 1 + 2 + 1 + 1 + 1                      # postprocess, keys, topk, gather, kde (symmetric + finish), balance, topk, gather
+        n += 1 + 1 + 1 + 1 + 5 + 1 + 1 + 1                      # postprocess, keys, topk, gather, kde (keys, sort, gather+boxes, symmetric, finish), balance, topk, gather
         n += (2 if self.n_hyp > 0 else 0) + 1 + 1               # init+ransac, refit, corner error
         return n
 

@@ -252,10 +252,12 @@ def test_kde_symmetric_kernel(gf):
     for m in (20000, 5000, 2177, 128, 129, 1):
         x = synth.make_matches(synth.random_homography(cgen), m, gen, "cuda")
         ref = oracle.kde_def(x.cpu(), 0.1)
-        a = gf.kde(x, 0.1, half=False, algo=KDE_SYMMETRIC)
-        _close(a, ref, rtol=1e-4, atol_rel=0)
-        _close(a, gf.kde(x, 0.1, half=False, algo=KDE_FULL), rtol=2e-5, atol_rel=0)
-        assert torch.equal(a, gf.kde(x, 0.1, half=False, algo=KDE_SYMMETRIC))
+        full = gf.kde(x, 0.1, half=False, algo=KDE_FULL)
+        for cut in (None, 0.0, 5.0):      # default 7-sigma cut-off (Morton sort + block boxes), every pair, tighter cut
+            a = gf.kde(x, 0.1, half=False, algo=KDE_SYMMETRIC, cut_sigmas=cut)
+            _close(a, ref, rtol=1e-4, atol_rel=0)
+            _close(a, full, rtol=2e-5 if cut != 5.0 else 1e-4, atol_rel=0)
+            assert torch.equal(a, gf.kde(x, 0.1, half=False, algo=KDE_SYMMETRIC, cut_sigmas=cut))
     xb = torch.stack([synth.make_matches(synth.random_homography(cgen), 3333, gen, "cuda") for _ in range(3)])
     outb = gf.kde(xb, 0.1, half=False, algo=KDE_SYMMETRIC)
     for i in range(3):

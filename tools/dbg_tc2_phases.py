@@ -14,10 +14,14 @@ for (s, c, hs, g, r) in synth.pyramid_config(448) + synth.pyramid_config(448, up
         continue
     f0, f1, flow = synth.scale_inputs(Hs, c, hs, g, gen, "cuda")
     out = torch.empty((b, (2 * r + 1) ** 2, g, g), device="cuda")
-    algo = 5 | (256 << 4)
-    gf.local_correlation((b, c, hs, hs), f0, f1, r, g, flow=flow, algo=algo, out=out)
-    local_correlation_v2_counters(reset=True)
-    gf.local_correlation((b, c, hs, hs), f0, f1, r, g, flow=flow, algo=algo, out=out)
-    cnt = local_correlation_v2_counters(reset=True)
-    n = max(cnt[7], 1)
-    print(f"scale {s} hs {hs} G {g}: chunks/CTA-warp0 total {cnt[7]}, clocks per chunk: wait {cnt[4]/n:.0f} pull {cnt[5]/n:.0f} rows {cnt[6]/n:.0f}; gather pts {cnt[1]} tiles {cnt[2]}")
+    for dbg in (1, 3, 5, 7):
+        algo = 5 | ((256 * dbg) << 4)
+        gf.local_correlation((b, c, hs, hs), f0, f1, r, g, flow=flow, algo=algo, out=out)
+        local_correlation_v2_counters(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gf.local_correlation((b, c, hs, hs), f0, f1, r, g, flow=flow, algo=algo, out=out)
+        e1.record()
+        cnt = local_correlation_v2_counters(reset=True)
+        n = max(cnt[7], 1)
+        print(f"scale {s} hs {hs} G {g} dbg {dbg}: {e0.elapsed_time(e1)*1e3:.0f} us; clocks per chunk: wait {cnt[4]/n:.0f} pull {cnt[5]/n:.0f} rows {cnt[6]/n:.0f}; gather pts {cnt[1]} tiles {cnt[2]}")
