@@ -43,7 +43,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -290,7 +290,7 @@ def main():
         args.warmup = 1 if args.warmup is None else min(args.warmup, 2)
         run_reference(args)
     else:
-        args.steps = 20 if args.steps is None else args.steps
+        args.steps = 40 if args.steps is None else args.steps
         args.warmup = 3 if args.warmup is None else args.warmup
         run_ours(args)
 
