@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_kernel(HgParams p) {
 }
 
 // ---- block reduction of NACC doubles: result in sm_out[0..NACC) ---------------------------------
-constexpr int RF_THREADS = 256;
+constexpr int RF_THREADS = 512;
 template <int NACC>
 __device__ void block_reduce(double (&acc)[NACC], double* sm_part /*[RF_THREADS/32][NACC]*/, double* sm_out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -487,8 +487,9 @@ __global__ void __launch_bounds__(256) lc_prep_plan_kernel(const LcParams p, con
 }
 
 // single-thread roles poll with a back-off so that they do not steal issue slots from the epilogue warps
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, bool spin = false) {
+    while (!mbar_try_wait(bar, parity))
+        if (!spin) __nanosleep(32);
 }
 __device__ __forceinline__ void st_stream_pred(float* ptr, float v, bool pred) {
     // no "memory" clobber: the outputs are never read back, and the compiler must stay free to hoist the staging reads
@@ -558,7 +559,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                 const int pre = min(nchunks, c.nstb);
                 for (int ch = 0; ch < nchunks; ++ch, ++q) {
                     if (ch == pre) {
-                        mbar_wait_sleep(a_empty, (tt & 1) ^ 1);
+                        mbar_wait_sleep(a_empty, (tt & 1) ^ 1, p.debug & 32);
                         mbar_expect_tx(a_full, A_STAGE);
 #pragma unroll
                         for (int at = 0; at < ATOMS; ++at)
@@ -569,7 +570,8 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                             }
                     }
                     const uint32_t s = q % c.nstb;
-                    mbar_wait_sleep(&b_empty[s], ((q / c.nstb) & 1) ^ 1);
+                    mbar_wait_sleep(&b_empty[s], ((q / c.nstb) & 1) ^ 1, p.debug & 32);
+                    if (p.debug & 8) { mbar_arrive(&b_full[s]); continue; }
                     mbar_expect_tx(&b_full[s], b_bytes);
 #pragma unroll
                     for (int at = 0; at < ATOMS; ++at)
@@ -577,7 +579,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                                     d.y0 + ch * RPS, b);
                 }
                 if (pre == nchunks) {                  // short tile: every B stage went out first
-                    mbar_wait_sleep(a_empty, (tt & 1) ^ 1);
+                    mbar_wait_sleep(a_empty, (tt & 1) ^ 1, p.debug & 32);
                     mbar_expect_tx(a_full, A_STAGE);
 #pragma unroll
                     for (int at = 0; at < ATOMS; ++at)
@@ -598,19 +600,19 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
             for (int tile = blockIdx.x; tile < c.ntiles; tile += gridDim.x) {
                 const TileDesc d = plan[tile];
                 if (d.flags) continue;
-                mbar_wait_sleep(a_full, tt & 1);
+                mbar_wait_sleep(a_full, tt & 1, p.debug & 32);
                 const int nchunks = (d.nrows + RPS - 1) / RPS;
                 const uint32_t idesc = idesc_bf16(RPS * (NBW_FIRST + 8 * d.bwi));
                 for (int ch = 0; ch < nchunks; ++ch, ++q) {
                     const uint32_t s = q % c.nstb, acc = q % NACC;
-                    mbar_wait_sleep(&b_full[s], (q / c.nstb) & 1);
-                    mbar_wait_sleep(&d_empty[acc], ((q / NACC) & 1) ^ 1);
+                    mbar_wait_sleep(&b_full[s], (q / c.nstb) & 1, p.debug & 32);
+                    mbar_wait_sleep(&d_empty[acc], ((q / NACC) & 1) ^ 1, p.debug & 32);
                     fence_after_sync();
                     const uint32_t b_addr = smem_u32(b_base + (size_t)s * B_STAGE);
                     const uint32_t dt = tmem_base + acc * (uint32_t)NMAX;
                     uint32_t accum = 0;
 #pragma unroll
-                    for (int combo = 0; combo < 3; ++combo) {
+                    for (int combo = (p.debug & 16) ? 3 : 0; combo < 3; ++combo) {
                         const int pa = combo == 2 ? 1 : 0, pb = combo == 1 ? 1 : 0;   // lo*hi, hi*lo, then hi*hi last
 #pragma unroll
                         for (int ks = 0; ks < NKS; ++ks) {
@@ -974,8 +976,9 @@ extern "C" int gfb_local_corr_tc2_f32(const float* f0, const float* f1, const fl
     int rc = fill_params(p, f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset);
     if (rc != GFB_OK) return rc;
     GFB_CHECK_ARG(group >= 0);
-    p.debug = (group >> 8) & 7;                // profiling aids: bit 0 per-phase clocks of epilogue warp 0 into the debug counters,
-                                               // bit 1 suppress the output stores, bit 2 skip the staging stores (results are wrong)
+    p.debug = (group >> 8) & 63;               // profiling aids: bit 0 per-phase clocks of epilogue warp 0 into the debug counters,
+                                               // bit 1 suppress the output stores, bit 2 skip the staging stores, bit 3 skip the B loads,
+                                               // bit 4 skip the MMAs (results are wrong with bits 1-4)
     group &= 255;
     cudaStream_t st = gfb_cu(stream);
 #define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, group);
