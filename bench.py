@@ -242,9 +242,15 @@ def run_ours(args):
                 by_scale[k] = {"GBps": nb / t_ms / 1e6 if t_ms else None, "frac": nb / t_ms / 1e6 / peaks["hbm_gbs"] if t_ms else None,
                                "ms_per_step": t_ms}
         achieved = lc_bytes * args.steps / (lc_ms / 1e3) / 1e9 if lc_ms else None
+        traffic = None                     # DRAM bytes of the same launches from the committed ncu capture (tools/lc_traffic.py)
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_lc_dram_traffic.json")))["dram_bytes_per_step"]
+        except Exception:
+            pass
         roofline = {"kernel": "local_correlation: lc_tc2_kernel (+ lc_prep_plan_kernel) at C >= 32, lc_pt_kernel at C = 16; all scales/iterations/passes of a step", "bound": "hbm",
                     "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": src, "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"] if achieved else None, "traffic": None,
+                    "frac": achieved / peaks["hbm_gbs"] if achieved else None, "traffic": traffic,
+                    "traffic_source": "profiles/r1_lc_dram_traffic.json (ncu dram__bytes_read+write, all 14 calls of a step)" if traffic else None,
                     "algorithmic_bytes_per_step": lc_bytes, "launches_per_step": n_lc // max(args.steps, 1),
                     "share_of_step": lc_ms / total_ms if total_ms else None, "by_scale": by_scale}
         # CPU baseline on this box's host cores: bounded sample (1 pair x 2 steps)

@@ -68,3 +68,20 @@ def test_synthetic_batch_shapes_and_algorithmic_bytes():
     assert abs(p1 / 1e6 - 12.739) < 0.01 and abs(p2 / 1e6 - 17.632) < 0.01
     b = synth.PairBatch(1, device="cpu")
     assert b.final_flow.shape == (2, 2, 320, 320) and len(b.passes) == 2
+
+
+def test_launch_accounting_and_workspace_queries():
+    """Host-only entry points: launch count of the default local_correlation path and workspace sizes."""
+    from gfnet_b200 import synth
+    from gfnet_b200._lib import lib
+    from gfnet_b200.ops import local_correlation_launches
+    from gfnet_b200.pipeline import HotPath
+    # C >= 32: fused pre-pass + main kernel, one pair per call; C = 16: one persistent kernel
+    assert local_correlation_launches(64, 64, 32, 32, 32, 7) == 2
+    assert local_correlation_launches(64, 32, 140, 140, 80, 4) == 2
+    assert local_correlation_launches(64, 16, 224, 224, 128, 2) == 1
+    assert lib.gfb_local_corr_tc2_groups(64, 32, 140, 140, 80, 16) == 4        # explicit groups of 16 elements
+    assert lib.gfb_local_corr_tc2_workspace_bytes(64, 32, 140, 140, 80, 4, 0) > 64 * (140 * 140 + 80 * 80) * 32 * 4
+    assert lib.gfb_kde_sym_workspace_bytes(32, 20000) >= 32 * 20000 * (8 + 4 + 8 + 16)
+    batch = synth.PairBatch(1, num_itr=2, device="cpu")
+    assert HotPath().kernel_launches(batch) == 41
