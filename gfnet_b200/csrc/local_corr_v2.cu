@@ -487,9 +487,19 @@ __global__ void __launch_bounds__(256) lc_prep_plan_kernel(const LcParams p, con
 }
 
 // single-thread roles poll with a back-off so that they do not steal issue slots from the epilogue warps
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, bool spin = false) {
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, int mode = 0) {
+    if (mode & 128) { while (!mbar_test_wait(bar, parity)) { } return; }     // debug: non-blocking test in a tight loop
     while (!mbar_try_wait(bar, parity))
-        if (!spin) __nanosleep(32);
+        if (!(mode & 32)) __nanosleep(32);
 }
 __device__ __forceinline__ void st_stream_pred(float* ptr, float v, bool pred) {
     // no "memory" clobber: the outputs are never read back, and the compiler must stay free to hoist the staging reads
@@ -507,15 +517,17 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
     constexpr int NKS = C / 16;                              // K = 16 steps per part
     constexpr uint32_t A_ATOM = 128 * 128, B_ATOM = NMAX * 128;
     constexpr uint32_t A_STAGE = ATOMS * A_ATOM, B_STAGE = ATOMS * B_ATOM;
+    constexpr int NSTA = C <= 32 ? 2 : 1;                    // A tiles in shared memory (two where they fit: the next tile's A
+                                                             // arrives while this tile still runs)
     static_assert(W <= LDW, "window wider than the TMEM pull");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* a_base = smem;
-    unsigned char* b_base = smem + A_STAGE;
+    unsigned char* b_base = smem + NSTA * A_STAGE;
     float* ebuf = reinterpret_cast<float*>(b_base + (size_t)c.nstb * B_STAGE);     // [EPI_WARPS][LDW][32 lanes]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ebuf + EPI_WARPS * LDW * 32);
-    uint64_t* a_full = bars;               // [1]
-    uint64_t* a_empty = a_full + 1;        // [1]
-    uint64_t* b_full = a_empty + 1;        // [nstb <= 6]
+    uint64_t* a_full = bars;               // [NSTA <= 2]
+    uint64_t* a_empty = a_full + 2;        // [NSTA]
+    uint64_t* b_full = a_empty + 2;        // [nstb <= 6]
     uint64_t* b_empty = b_full + 6;        // [nstb]
     uint64_t* d_full = b_empty + 6;        // [NACC]
     uint64_t* d_empty = d_full + NACC;     // [NACC]
@@ -527,7 +539,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) __trap();          // the swizzled operand stages need 1024-byte alignment
-        mbar_init(a_full, 1); mbar_init(a_empty, 1);
+        for (int s = 0; s < NSTA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < c.nstb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < NACC; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], EPI_WARPS); }
         mbar_fence_init();
@@ -556,21 +568,24 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                 const uint32_t b_bytes = (uint32_t)(ATOMS * RPS * (NBW_FIRST + 8 * d.bwi) * 128);
                 // the first B stages of this tile go out before its A tile: the A buffer is free only when the previous
                 // tile's last MMA has retired, the B ring usually has room earlier
-                const int pre = min(nchunks, c.nstb);
+                // (with two A buffers the A tile simply goes first)
+                const int pre = NSTA > 1 ? 0 : min(nchunks, c.nstb);
+                const uint32_t as = tt % NSTA, aph = (tt / NSTA) & 1;
+                unsigned char* a_dst = a_base + as * A_STAGE;
                 for (int ch = 0; ch < nchunks; ++ch, ++q) {
                     if (ch == pre) {
-                        mbar_wait_sleep(a_empty, (tt & 1) ^ 1, p.debug & 32);
-                        mbar_expect_tx(a_full, A_STAGE);
+                        mbar_wait_sleep(&a_empty[as], aph ^ 1, p.debug);
+                        mbar_expect_tx(&a_full[as], A_STAGE);
 #pragma unroll
                         for (int at = 0; at < ATOMS; ++at)
                             for (int w = 0; w < 4; ++w) {
                                 const int bx = w % c.nbx, by = w / c.nbx;
-                                tma_load_4d(a_base + at * A_ATOM + w * 4096, &tmapA, a_full, at * 32,
+                                tma_load_4d(a_dst + at * A_ATOM + w * 4096, &tmapA, &a_full[as], at * 32,
                                             tx * (c.nbx * c.blx) + bx * c.blx, ty * (c.nby * c.bly) + by * c.bly, b);
                             }
                     }
                     const uint32_t s = q % c.nstb;
-                    mbar_wait_sleep(&b_empty[s], ((q / c.nstb) & 1) ^ 1, p.debug & 32);
+                    mbar_wait_sleep(&b_empty[s], ((q / c.nstb) & 1) ^ 1, p.debug);
                     if (p.debug & 8) { mbar_arrive(&b_full[s]); continue; }
                     mbar_expect_tx(&b_full[s], b_bytes);
 #pragma unroll
@@ -579,13 +594,13 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                                     d.y0 + ch * RPS, b);
                 }
                 if (pre == nchunks) {                  // short tile: every B stage went out first
-                    mbar_wait_sleep(a_empty, (tt & 1) ^ 1, p.debug & 32);
-                    mbar_expect_tx(a_full, A_STAGE);
+                    mbar_wait_sleep(&a_empty[as], aph ^ 1, p.debug);
+                    mbar_expect_tx(&a_full[as], A_STAGE);
 #pragma unroll
                     for (int at = 0; at < ATOMS; ++at)
                         for (int w = 0; w < 4; ++w) {
                             const int bx = w % c.nbx, by = w / c.nbx;
-                            tma_load_4d(a_base + at * A_ATOM + w * 4096, &tmapA, a_full, at * 32,
+                            tma_load_4d(a_dst + at * A_ATOM + w * 4096, &tmapA, &a_full[as], at * 32,
                                         tx * (c.nbx * c.blx) + bx * c.blx, ty * (c.nby * c.bly) + by * c.bly, b);
                         }
                 }
@@ -596,17 +611,18 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
         // ================= MMA issuer =================
         if (lane == 0) {
             uint32_t q = 0, tt = 0;
-            const uint32_t a_addr = smem_u32(a_base);
             for (int tile = blockIdx.x; tile < c.ntiles; tile += gridDim.x) {
                 const TileDesc d = plan[tile];
                 if (d.flags) continue;
-                mbar_wait_sleep(a_full, tt & 1, p.debug & 32);
+                const uint32_t as = tt % NSTA;
+                const uint32_t a_addr = smem_u32(a_base + as * A_STAGE);
+                mbar_wait_sleep(&a_full[as], (tt / NSTA) & 1, p.debug);
                 const int nchunks = (d.nrows + RPS - 1) / RPS;
                 const uint32_t idesc = idesc_bf16(RPS * (NBW_FIRST + 8 * d.bwi));
                 for (int ch = 0; ch < nchunks; ++ch, ++q) {
                     const uint32_t s = q % c.nstb, acc = q % NACC;
-                    mbar_wait_sleep(&b_full[s], (q / c.nstb) & 1, p.debug & 32);
-                    mbar_wait_sleep(&d_empty[acc], ((q / NACC) & 1) ^ 1, p.debug & 32);
+                    mbar_wait_sleep(&b_full[s], (q / c.nstb) & 1, p.debug);
+                    mbar_wait_sleep(&d_empty[acc], ((q / NACC) & 1) ^ 1, p.debug);
                     fence_after_sync();
                     const uint32_t b_addr = smem_u32(b_base + (size_t)s * B_STAGE);
                     const uint32_t dt = tmem_base + acc * (uint32_t)NMAX;
@@ -625,7 +641,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                     }
                     mma_commit(&b_empty[s]);
                     mma_commit(&d_full[acc]);
-                    if (ch + 1 == nchunks) mma_commit(a_empty);
+                    if (ch + 1 == nchunks) mma_commit(&a_empty[as]);
                 }
                 ++tt;
             }
@@ -755,17 +771,19 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                 const bool more = ch + 1 < nchunks;
                 const uint32_t nacc = (q + 1) % NACC;
                 if (more) {
-                    mbar_wait(&d_full[nacc], ((q + 1) / NACC) & 1);
+                    if (p.debug & 128) { while (!mbar_test_wait(&d_full[nacc], ((q + 1) / NACC) & 1)) { } }
+                    else mbar_wait(&d_full[nacc], ((q + 1) / NACC) & 1);
                     fence_after_sync();
                     activity(ch + 1);
                 }
                 const long long c2 = dbg ? clock64() : 0;
+                const bool emit = !(p.debug & 64);     // bit 6: pulls and hand-offs only
                 if (hA) stage(rA);
                 if (more && anyA) tmem_ld32(tlane + nacc * (uint32_t)NMAX, rA);
-                if (hA) emit_row(cj, cA);
+                if (hA && emit) emit_row(cj, cA);
                 if (hB) stage(rB);
                 if (more && anyB) tmem_ld32(tlane + nacc * (uint32_t)NMAX + (uint32_t)tbw, rB);
-                if (hB) emit_row(cj + 1, cB);
+                if (hB && emit) emit_row(cj + 1, cB);
                 if (more) release(nacc);
                 if (dbg) { const long long c3 = clock64(); dbg_wait += c2 - c1; dbg_rows += c3 - c2; ++dbg_n; }
             }
@@ -820,7 +838,7 @@ static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size
     tc2_config(p0.G, p0.Ws, R, c);
     const int G = p0.G;
     const size_t a_stage = (size_t)ATOMS * 128 * 128, b_stage = (size_t)ATOMS * NMAX * 128;
-    const size_t fixed = a_stage + (size_t)EPI_WARPS * LDW * 32 * sizeof(float) + 24 * sizeof(uint64_t);
+    const size_t fixed = (C <= 32 ? 2 : 1) * a_stage + (size_t)EPI_WARPS * LDW * 32 * sizeof(float) + 24 * sizeof(uint64_t);
     const size_t budget = 112 * 1024 + 256;                // two CTAs per SM
     c.nstb = (int)min((size_t)6, (budget - fixed) / b_stage);
     if (c.nstb < 2) return GFB_EUNSUPPORTED;
@@ -976,7 +994,7 @@ extern "C" int gfb_local_corr_tc2_f32(const float* f0, const float* f1, const fl
     int rc = fill_params(p, f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset);
     if (rc != GFB_OK) return rc;
     GFB_CHECK_ARG(group >= 0);
-    p.debug = (group >> 8) & 63;               // profiling aids: bit 0 per-phase clocks of epilogue warp 0 into the debug counters,
+    p.debug = (group >> 8) & 255;               // profiling aids: bit 0 per-phase clocks of epilogue warp 0 into the debug counters,
                                                // bit 1 suppress the output stores, bit 2 skip the staging stores, bit 3 skip the B loads,
                                                // bit 4 skip the MMAs (results are wrong with bits 1-4)
     group &= 255;

@@ -87,7 +87,9 @@ int gfb_local_corr_tc_f32(const float* f0, const float* f1, const float* flow, f
  *   rows [bf16 hi(C) | bf16 lo(C)] into `workspace` (processed in groups of `group` batch elements so that the
  *   workspace stays L2-resident; 0 = auto), the main kernel accumulates hi*hi + hi*lo + lo*hi in fp32 (relative error
  *   ~1e-5, inside the 1e-4 fp32 bar).  (r, C) in {(4,32), (3,32), (6,64), (7,64), (5,64), (4,64)}; any Ws / pitch.
- *   workspace >= gfb_local_corr_tc2_workspace_bytes(...) bytes, 128-byte aligned.
+ *   workspace >= gfb_local_corr_tc2_workspace_bytes(...) bytes, 128-byte aligned.  Bits 8-15 of `group` are profiling
+ *   switches (per-phase clocks, suppress stores / staging / B loads / MMAs / row arithmetic, polling flavours): results
+ *   are only valid with those bits clear.
  * Both return GFB_EUNSUPPORTED for other (r, C); points whose windows leave the staged box use the exact gather. */
 int gfb_local_corr_pt_f32(const float* f0, const float* f1, const float* flow, float* out,
                           int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,

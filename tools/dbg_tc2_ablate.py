@@ -15,7 +15,7 @@ for (s, c, hs, g, r) in synth.pyramid_config(448) + synth.pyramid_config(448, up
     f0, f1, flow = synth.scale_inputs(Hs, c, hs, g, gen, "cuda")
     out = torch.empty((b, (2 * r + 1) ** 2, g, g), device="cuda")
     res = []
-    for dbg in (0, 32, 30, 62):
+    for dbg in (0, 128, 94, 222):
         algo = 5 | ((256 * dbg) << 4)
         ts = []
         for it in range(6):
@@ -27,4 +27,4 @@ for (s, c, hs, g, r) in synth.pyramid_config(448) + synth.pyramid_config(448, up
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3)
         res.append(sorted(ts)[2])
-    print(f"scale {s} hs {hs} G {g}: full {res[0]:.0f} us, full with tight polling {res[1]:.0f}, skeleton only {res[2]:.0f}, skeleton with tight polling {res[3]:.0f}")
+    print(f"scale {s} hs {hs} G {g}: full {res[0]:.0f} us, full with test_wait polling {res[1]:.0f}, bare skeleton {res[2]:.0f}, bare skeleton with test_wait polling {res[3]:.0f}")
