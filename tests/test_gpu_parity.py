@@ -132,6 +132,28 @@ def test_local_correlation_v2_kernels(gf, shape, kind):
             _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=ALGO_TC2 | (group << 4)), ref)
 
 
+@pytest.mark.parametrize("shape", [(16, 64, 32, 32, 7), (8, 64, 56, 32, 6), (4, 32, 112, 64, 4), (2, 16, 224, 128, 2),
+                                   (8, 64, 70, 40, 6), (4, 32, 140, 80, 4), (2, 16, 280, 160, 2)])
+def test_local_correlation_full_size_properties(gf, shape):
+    """BASELINE config 2 at full size (op batch 64): the auto-selected kernels against the per-sample gather kernel
+    (the reference's exact coordinate arithmetic, itself pinned to the oracle at small sizes), linearity in feature0,
+    and the zero-flow-independent identity corr(0, f1) = 0."""
+    from gfnet_b200 import synth
+    s, c, hs, G, r = shape
+    b = 64
+    gen = torch.Generator(device="cuda").manual_seed(100 + s + hs)
+    cgen = torch.Generator().manual_seed(21)
+    Hs = [synth.random_homography(cgen) for _ in range(b)]
+    f0, f1, flow = synth.scale_inputs(Hs, c, hs, G, gen, "cuda")
+    out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow)
+    ref = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=1)
+    _close(out, ref)
+    g0 = torch.randn(f0.shape, generator=gen, device="cuda")
+    lin = gf.local_correlation((b, c, hs, hs), f0 + 0.5 * g0, f1, r, G, flow=flow)
+    _close(lin, out + 0.5 * gf.local_correlation((b, c, hs, hs), g0, f1, r, G, flow=flow), rtol=2e-4, atol_rel=1e-4)
+    assert float(gf.local_correlation((b, c, hs, hs), torch.zeros_like(f0), f1, r, G, flow=flow).abs().max()) == 0.0
+
+
 def test_local_correlation_stream_kernel_is_used(gf):
     """algo=2 must run the TMA kernel (raises NotImplementedError if the shape is not eligible)."""
     from gfnet_b200 import synth
