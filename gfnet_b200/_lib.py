@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_HERE, "_C", "libgfnet_b200.so")
 EXPORTS = [
     "gfb_abi_version", "gfb_strerror", "gfb_device_info", "gfb_local_corr_f32", "gfb_avg_pool2_f32",
     "gfb_pad_rows_f32", "gfb_debug_local_corr_counters", "gfb_local_corr_tc_workspace_bytes", "gfb_local_corr_tc_f32", "gfb_local_corr_pt_f32",
-    "gfb_local_corr_tc2_workspace_bytes", "gfb_local_corr_tc2_f32", "gfb_debug_local_corr_v2_counters", "gfb_local_corr_tc2_groups",
+    "gfb_local_corr_tc2_workspace_bytes", "gfb_local_corr_tc2_f32", "gfb_debug_local_corr_v2_counters", "gfb_local_corr_tc2_groups", "gfb_local_corr_tc2_prepare_f32",
+    "gfb_local_corr_tc2_run_f32",
     "gfb_global_match_f32", "gfb_pos_embed_f32", "gfb_kde_f32", "gfb_kde_sym_workspace_bytes", "gfb_kde_sym_f32", "gfb_match_postprocess_f32",
     "gfb_sample_keys_f32", "gfb_balance_keys_f32", "gfb_gather_matches_f32", "gfb_topk_workspace_bytes",
     "gfb_topk_desc_f32", "gfb_homography_workspace_bytes", "gfb_homography_f32", "gfb_corner_error_f64",
@@ -46,6 +47,8 @@ def _load():
     lib.gfb_local_corr_tc2_workspace_bytes.restype = sz
     lib.gfb_local_corr_tc2_workspace_bytes.argtypes = [i32] * 7
     lib.gfb_local_corr_tc2_groups.argtypes = [i32] * 6
+    lib.gfb_local_corr_tc2_prepare_f32.argtypes = [vp, vp] + [i32] * 7 + [vp, sz, vp]
+    lib.gfb_local_corr_tc2_run_f32.argtypes = [vp, vp, vp, vp] + [i32] * 9 + [vp, sz, vp]
     lib.gfb_local_corr_tc2_f32.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp, sz, vp]
     lib.gfb_debug_local_corr_v2_counters.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), i32]
     lib.gfb_pad_rows_f32.argtypes = [vp, vp, i64, i32, i32, vp]

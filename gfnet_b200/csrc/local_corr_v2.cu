@@ -832,7 +832,9 @@ static int tc2_group(int B, size_t per_elem, int group) {
 }
 
 template <int R, int C>
-static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size_t ws_bytes, int group) {
+// phase 0: pre-pass + plan + main; 1: pre-pass only (feature0 / feature1 -> workspace); 2: plan + main on a workspace that
+// phase 1 filled (the features of a refiner scale do not change between its iterations, only the flow does)
+static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size_t ws_bytes, int group, int phase = 0) {
     constexpr int ATOMS = (2 * C * 2 + 127) / 128;
     TcCfg c;
     tc2_config(p0.G, p0.Ws, R, c);
@@ -847,6 +849,7 @@ static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size
 
     const size_t ws0_per = (size_t)G * G * C * 4, ws1_per = (size_t)p0.Hs * p0.Ws * C * 4;
     const int gb = tc2_group(p0.B, ws0_per + ws1_per, group);
+    if (phase != 0 && gb < p0.B) return GFB_EUNSUPPORTED;  // a prepared workspace holds the whole batch
     const size_t plan_bytes = align_up((size_t)gb * c.tiles_x * c.tiles_y * sizeof(TileDesc), 1024);
     const size_t need = plan_bytes + align_up(gb * ws0_per, 1024) + gb * ws1_per;
     if (!workspace || ws_bytes < need) return GFB_EWORKSPACE;
@@ -867,16 +870,17 @@ static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size
         p.B = min(gb, p0.B - b0);
         p.f0 = p0.f0 + (size_t)b0 * C * gg;
         p.f1 = p0.f1 + (size_t)b0 * C * plane;
-        p.flow = p0.flow + (size_t)b0 * 2 * gg;
-        p.out = p0.out + (size_t)b0 * p0.k_total * gg;
+        p.flow = p0.flow ? p0.flow + (size_t)b0 * 2 * gg : nullptr;
+        p.out = p0.out ? p0.out + (size_t)b0 * p0.k_total * gg : nullptr;
         c.ntiles = p.B * c.tiles_x * c.tiles_y;
 
-        const int nplan = (c.ntiles + 1) / 2;
+        const int nplan = phase == 1 ? 0 : (c.ntiles + 1) / 2;
         const size_t units = (size_t)p.B * (C / 16) * (gg + (size_t)p.Hs * p.Ws);
-        const int nprep = (int)min((size_t)sms * 5, (units + 255) / 256);    // one resident wave next to the short plan blocks
+        const int nprep = phase == 2 ? 0 : (int)min((size_t)sms * 5, (units + 255) / 256);    // one resident wave next to the short plan blocks
         lc_prep_plan_kernel<C><<<nplan + nprep, 256, 0, st>>>(p, c, plan, ws0, ws1, nplan);
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
+        if (phase == 1) continue;
 
         CUtensorMap tmapA;
         TmapSet tmapB;
@@ -976,6 +980,37 @@ extern "C" size_t gfb_local_corr_tc2_workspace_bytes(int B, int C, int Hs, int W
     const int gb = lcv2::tc2_group(B, ws0_per + ws1_per, group);
     return lcv2::align_up((size_t)gb * c.tiles_x * c.tiles_y * sizeof(lcv2::TileDesc), 1024) +
            lcv2::align_up(gb * ws0_per, 1024) + gb * ws1_per;
+}
+
+// Split form of gfb_local_corr_tc2_f32 for callers that correlate the same feature0 / feature1 against several flows
+// (the iterations of one refiner scale, model/network.py:230-281): prepare once, run per flow.
+extern "C" int gfb_local_corr_tc2_prepare_f32(const float* f0, const float* f1, int B, int C, int Hs, int Ws, int f1_pitch,
+                                              int G, int r, void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
+    LcParams p;
+    float dummy;
+    const int kk = (2 * r + 1) * (2 * r + 1);
+    int rc = fill_params(p, f0, f1, &dummy, &dummy, B, C, Hs, Ws, f1_pitch, G, r, kk, 0);
+    if (rc != GFB_OK) return rc;
+    p.flow = nullptr; p.out = nullptr;
+    cudaStream_t st = gfb_cu(stream);
+#define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, 0, 1);
+    GFB_TC2_CASE(4, 32) GFB_TC2_CASE(6, 64) GFB_TC2_CASE(7, 64) GFB_TC2_CASE(3, 32) GFB_TC2_CASE(5, 64) GFB_TC2_CASE(4, 64)
+#undef GFB_TC2_CASE
+    return GFB_EUNSUPPORTED;
+}
+
+extern "C" int gfb_local_corr_tc2_run_f32(const float* f0, const float* f1, const float* flow, float* out,
+                                          int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                                          int k_total, int k_offset,
+                                          void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
+    LcParams p;
+    int rc = fill_params(p, f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset);
+    if (rc != GFB_OK) return rc;
+    cudaStream_t st = gfb_cu(stream);
+#define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, 0, 2);
+    GFB_TC2_CASE(4, 32) GFB_TC2_CASE(6, 64) GFB_TC2_CASE(7, 64) GFB_TC2_CASE(3, 32) GFB_TC2_CASE(5, 64) GFB_TC2_CASE(4, 64)
+#undef GFB_TC2_CASE
+    return GFB_EUNSUPPORTED;
 }
 
 // number of (pre-pass, main) launch pairs gfb_local_corr_tc2_f32 issues for these shapes (bench.py's launch count)

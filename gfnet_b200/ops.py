@@ -40,9 +40,43 @@ def _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
             and (r, c) in _TC_SHAPES)
 
 
+class PreparedFeatures:
+    """feature0 / feature1 of one refiner scale rewritten once for the tcgen05 kernel (``local_correlation_prepare``);
+    pass it as ``prepared=`` to every ``local_correlation`` call of that scale (same features, different flow)."""
+
+    def __init__(self, size, f0, f1, r, G, wsbuf, nws):
+        self.size, self.f0, self.f1, self.r, self.G, self.wsbuf, self.nws = size, f0, f1, r, G, wsbuf, nws
+
+    def matches(self, size, f0, f1, r, G):
+        return (self.size == tuple(size) and self.r == r and self.G == G and self.f0.data_ptr() == f0.data_ptr()
+                and self.f1.data_ptr() == f1.data_ptr() and self.f0._version == f0._version and self.f1._version == f1._version)
+
+
+def local_correlation_prepare(featuremap_size, feature0, feature1, local_radius, num_grid):
+    """Hoist the feature pre-pass of the tcgen05 local-correlation kernel out of the iterations of a refiner scale
+    (the reference calls ``local_correlation`` ``num_itr`` times per scale with the same ``feature0`` / ``feature1``,
+    model/network.py:230-281).  Returns None when the shape is served by a kernel without a pre-pass."""
+    B, c, h, w = (int(v) for v in featuremap_size)
+    G, r = int(num_grid), int(local_radius)
+    if (r, c) not in _TC2_SHAPES:
+        return None
+    f0 = require_cuda_f32("feature0", feature0)
+    f1 = require_cuda_f32("feature1", feature1)
+    if f0.shape != (B, c, G, G) or f1.shape != (B, c, h, w):
+        raise ValueError("feature0 / feature1 do not match featuremap_size / num_grid")
+    if int(lib.gfb_local_corr_tc2_groups(B, c, h, w, G, 0)) != 1:
+        return None
+    nws = int(lib.gfb_local_corr_tc2_workspace_bytes(B, c, h, w, G, r, 0))
+    wsbuf = torch.empty(nws, device=f0.device, dtype=torch.uint8)
+    with torch.cuda.device(f0.device):
+        check(lib.gfb_local_corr_tc2_prepare_f32(ptr(f0), ptr(f1), B, c, h, w, 0, G, r, ptr(wsbuf), nws, stream_ptr(f0.device)),
+              "local_correlation_prepare")
+    return PreparedFeatures((B, c, h, w), f0, f1, r, G, wsbuf, nws)
+
+
 def local_correlation(featuremap_size, feature0, feature1, local_radius, num_grid,
                       padding_mode="zeros", flow=None, im_A_coords=None, sample_mode="bilinear",
-                      grid_based_correlation=False, num_level=1, *, algo=ALGO_AUTO, out=None):
+                      grid_based_correlation=False, num_level=1, *, algo=ALGO_AUTO, out=None, prepared=None):
     """Flow-displaced (2r+1)^2 window correlation; reference: utils/local_correlation.py:4-72.
 
     ``feature0 [B,c,G,G]``, ``feature1 [B,c,h,w]``, ``flow [B,2,G,G]`` (or None: identity lattice,
@@ -85,6 +119,12 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
             src, pitch = f1, 0
             base = int(algo) & 15
             plain = _tc_eligible_modes(win_h, win_w, hs, ws, sample_mode, padding_mode)
+            if (prepared is not None and level == 0 and num_level == 1 and plain and int(algo) == ALGO_AUTO
+                    and prepared.matches((B, c, h, w), f0, f1, r, G)):
+                rc = lib.gfb_local_corr_tc2_run_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r, kk, 0,
+                                                    ptr(prepared.wsbuf), prepared.nws, st)
+                check(rc, "local_correlation (tcgen05, prepared features)")
+                continue
             if base == ALGO_TC2 or (int(algo) == ALGO_AUTO and plain and (r, c) in _TC2_SHAPES):
                 if not (plain and (r, c) in _TC2_SHAPES):
                     raise NotImplementedError("local_correlation: the TMA-fed tcgen05 kernel covers bilinear/zeros with "
@@ -275,10 +315,18 @@ def pos_embed(corr):
     return flow
 
 
-def local_correlation_launches(B, c, hs, ws, G, r):
-    """Kernels one default-mode local_correlation call launches for a GFNet-style call (bilinear, zeros, window = f1)."""
+def local_correlation_launches(B, c, hs, ws, G, r, calls=1):
+    """Kernels `calls` default-mode local_correlation calls on the same features launch (bilinear, zeros, window = f1);
+    with calls > 1 the tcgen05 shapes use ``local_correlation_prepare`` once."""
     if (r, c) in _TC2_SHAPES:
-        return 2 * int(lib.gfb_local_corr_tc2_groups(B, c, hs, ws, G, 0))     # fused pre-pass + plan, main kernel
+        groups = int(lib.gfb_local_corr_tc2_groups(B, c, hs, ws, G, 0))
+        if calls > 1 and groups == 1:
+            return 1 + 2 * calls                                              # pre-pass once, then plan + main per flow
+        return 2 * groups * calls                                             # fused pre-pass + plan, main kernel
+    return calls * _other_launches(c, r, hs, ws)
+
+
+def _other_launches(c, r, hs, ws):
     n = 1
     if ws % 4 and ((r, c) in _PT_AUTO or _stream_eligible(c, r, hs, ws, hs, ws, "bilinear", "zeros")):
         n += 1                                                                # pad_rows
@@ -295,5 +343,5 @@ def global_match_flops(B, C, N0, N1):
 
 
 __all__ = ["local_correlation", "kde", "coarse_match", "corr_volume", "pos_embed", "LazyCorrVolume",
-           "local_correlation_bytes", "local_correlation_launches", "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_STREAM", "ALGO_TC",
+           "local_correlation_bytes", "local_correlation_launches", "local_correlation_prepare", "PreparedFeatures", "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_STREAM", "ALGO_TC",
            "ALGO_PT", "ALGO_TC2"]

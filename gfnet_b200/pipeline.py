@@ -30,7 +30,7 @@ class HotPath:
         for p in batch.passes:                                  # local_corr: 1 launch (point kernel) or 2 per workspace group
             for sc in p:
                 b = sc["f1"].shape[0]
-                n += len(sc["flows"]) * ops.local_correlation_launches(b, sc["c"], sc["hs"], sc["hs"], sc["G"], sc["r"])
+                n += ops.local_correlation_launches(b, sc["c"], sc["hs"], sc["hs"], sc["G"], sc["r"], calls=len(sc["flows"]))
         n += 1 + 1 + 1 + 1 + 5 + 1 + 1 + 1                      # postprocess, keys, topk, gather, kde (keys, sort, gather+boxes, symmetric, finish), balance, topk, gather
         n += (2 if self.n_hyp > 0 else 0) + 1 + 1               # init+ransac, refit, corner error
         return n
@@ -41,12 +41,18 @@ class HotPath:
         for pi, scales in enumerate(batch.passes):
             for sc in scales:
                 b, c, hs, G, r = sc["f1"].shape[0], sc["c"], sc["hs"], sc["G"], sc["r"]
+                # the features of a scale are the same in every refiner iteration (model/network.py:230-281): their
+                # pre-pass is hoisted out of the iteration loop (and timed with the first call)
+                prep = None
                 for it, flow in enumerate(sc["flows"]):
                     buf = self._corr_buf((pi, sc["scale"]), (b, (2 * r + 1) ** 2, G, G), flow.device)
                     if self.timing is not None:
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         e0.record()
-                    ops.local_correlation((b, c, hs, hs), sc["f0"], sc["f1"], r, G, flow=flow, algo=self.lc_algo, out=buf)
+                    if it == 0 and len(sc["flows"]) > 1:
+                        prep = ops.local_correlation_prepare((b, c, hs, hs), sc["f0"], sc["f1"], r, G)
+                    ops.local_correlation((b, c, hs, hs), sc["f0"], sc["f1"], r, G, flow=flow, algo=self.lc_algo, out=buf,
+                                          prepared=prep)
                     if self.timing is not None:
                         e1.record()
                         self.timing.append((f"pass{pi + 1}_scale{sc['scale']}", e0, e1))

@@ -95,6 +95,16 @@ int gfb_local_corr_pt_f32(const float* f0, const float* f1, const float* flow, f
                           int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                           int k_total, int k_offset, int tune, gfb_stream_t stream);
 size_t gfb_local_corr_tc2_workspace_bytes(int B, int C, int Hs, int Ws, int G, int r, int group);
+/* Split form for callers that correlate the same feature0 / feature1 against several flows -- the iterations of one
+ * refiner scale (model/network.py:230-281 calls local_correlation num_itr times per scale with unchanged features):
+ * `prepare` runs the pre-pass into `workspace` (whole batch in one group, else GFB_EUNSUPPORTED), `run` plans and
+ * correlates one flow against it; f0 / f1 are still passed to `run` for the exact-gather fallback. */
+int gfb_local_corr_tc2_prepare_f32(const float* f0, const float* f1, int B, int C, int Hs, int Ws, int f1_pitch,
+                                   int G, int r, void* workspace, size_t workspace_bytes, gfb_stream_t stream);
+int gfb_local_corr_tc2_run_f32(const float* f0, const float* f1, const float* flow, float* out,
+                               int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                               int k_total, int k_offset,
+                               void* workspace, size_t workspace_bytes, gfb_stream_t stream);
 /* how many (pre-pass, main) launch pairs one gfb_local_corr_tc2_f32 call issues for these shapes */
 int gfb_local_corr_tc2_groups(int B, int C, int Hs, int Ws, int G, int group);
 /* Debug aid (synchronises): host_out8 = {lc_pt points on the global-memory path, lc_tc2 points on the gather path,

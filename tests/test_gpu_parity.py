@@ -130,6 +130,15 @@ def test_local_correlation_v2_kernels(gf, shape, kind):
     if c >= 32:
         for group in (0, 1, 2):
             _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=ALGO_TC2 | (group << 4)), ref)
+        # hoisted pre-pass: prepare once, correlate two different flows against the same features
+        prep = gf.local_correlation_prepare((b, c, hs, hs), f0, f1, r, G)
+        assert prep is not None
+        _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, prepared=prep), ref)
+        flow2 = (flow + 0.01).contiguous()
+        ref2 = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow2.cpu())
+        _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow2, prepared=prep), ref2)
+        f0b = f0.clone()          # other tensors: the handle does not match and the call runs its own pre-pass
+        _close(gf.local_correlation((b, c, hs, hs), f0b, f1, r, G, flow=flow, prepared=prep), ref)
 
 
 @pytest.mark.parametrize("shape", [(16, 64, 32, 32, 7), (8, 64, 56, 32, 6), (4, 32, 112, 64, 4), (2, 16, 224, 128, 2),

@@ -84,4 +84,5 @@ def test_launch_accounting_and_workspace_queries():
     assert lib.gfb_local_corr_tc2_workspace_bytes(64, 32, 140, 140, 80, 4, 0) > 64 * (140 * 140 + 80 * 80) * 32 * 4
     assert lib.gfb_kde_sym_workspace_bytes(32, 20000) >= 32 * 20000 * (8 + 4 + 8 + 16)
     batch = synth.PairBatch(1, num_itr=2, device="cpu")
-    assert HotPath().kernel_launches(batch) == 41
+    assert local_correlation_launches(64, 32, 140, 140, 80, 4, calls=2) == 5    # pre-pass hoisted: 1 + 2 x (plan, main)
+    assert HotPath().kernel_launches(batch) == 46
