@@ -120,12 +120,13 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_kernel(HgParams p) {
     if (!ok) return;                   // the same decision in all RS_SPLIT threads of the hypothesis
     int cnt = 0;
     for (int i = sub; i < p.N; i += RS_SPLIT) {
+        // |proj(X) - x|^2 <= thr^2 without the division: multiply through by den^2 (fp64 divisions dominate otherwise)
         const float4 q = spts[i];
         const double X = q.x, Y = q.y;
-        const double ww = 1.0 / (h[6] * X + h[7] * Y + 1.0);
-        const double dx = (h[0] * X + h[1] * Y + h[2]) * ww - (double)q.z;
-        const double dy = (h[3] * X + h[4] * Y + h[5]) * ww - (double)q.w;
-        cnt += (dx * dx + dy * dy <= (double)p.thr2);
+        const double den = h[6] * X + h[7] * Y + 1.0;
+        const double ex = (h[0] * X + h[1] * Y + h[2]) - (double)q.z * den;
+        const double ey = (h[3] * X + h[4] * Y + h[5]) - (double)q.w * den;
+        cnt += (ex * ex + ey * ey <= (double)p.thr2 * den * den) && den != 0.0;
     }
     // the RS_SPLIT threads of a hypothesis are consecutive lanes of one warp
     const unsigned gmask = ((1u << RS_SPLIT) - 1u) << ((threadIdx.x & 31) / RS_SPLIT * RS_SPLIT);
