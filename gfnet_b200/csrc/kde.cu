@@ -138,7 +138,7 @@ constexpr float KS_FIX = 1099511627776.f;   // 2^40
 
 __device__ __forceinline__ unsigned long long kde_fix(float v) { return __float2ull_rn(v * KS_FIX); }
 
-// Optional cut-off (cut2 > 0): the points arrive sorted along a Morton curve, bb holds the bounding box of every
+// Optional cut-off (cut2 > 0): the points arrive sorted along a Hilbert curve, bb holds the bounding box of every
 // 128-point block, and a tile pair whose boxes are further apart than the cut-off radius is skipped -- each of its
 // terms is below exp(-cut_sigmas^2 / 2) (2.3e-11 at 7 sigma, far below one fp32 ulp of a density that is >= 1).
 __device__ __forceinline__ float bb_dist2(const float* __restrict__ a, const float* __restrict__ b) {
@@ -296,18 +296,24 @@ __global__ void __launch_bounds__(256) kde_finish_kernel(const unsigned long lon
     }
 }
 
-// Morton code (10 + 10 bits) of the first two coordinates as an exactly representable float sort key
+// Hilbert-curve index (10 + 10 bits) of the first two coordinates as an exactly representable float sort key.  Unlike
+// the Morton curve the Hilbert curve never jumps, so ANY 128 consecutive points are spatially compact (tight boxes).
 __global__ void __launch_bounds__(256) kde_keys_kernel(const float4* __restrict__ x, float* __restrict__ keys, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = __ldg(x + i);
         uint32_t qx = (uint32_t)fminf(fmaxf((v.x + 1.f) * 511.5f, 0.f), 1023.f);
         uint32_t qy = (uint32_t)fminf(fmaxf((v.y + 1.f) * 511.5f, 0.f), 1023.f);
-        auto spread = [](uint32_t a) {
-            a = (a | (a << 8)) & 0x00FF00FFu; a = (a | (a << 4)) & 0x0F0F0F0Fu;
-            a = (a | (a << 2)) & 0x33333333u; a = (a | (a << 1)) & 0x55555555u;
-            return a;
-        };
-        keys[i] = (float)(spread(qx) | (spread(qy) << 1));
+        uint32_t d = 0;
+#pragma unroll
+        for (uint32_t sbit = 512; sbit > 0; sbit >>= 1) {
+            const uint32_t rx = (qx & sbit) ? 1u : 0u, ry = (qy & sbit) ? 1u : 0u;
+            d += sbit * sbit * ((3u * rx) ^ ry);
+            if (ry == 0) {
+                if (rx == 1) { qx = 1023u - qx; qy = 1023u - qy; }
+                const uint32_t t = qx; qx = qy; qy = t;
+            }
+        }
+        keys[i] = (float)d;
     }
 }
 
@@ -380,7 +386,7 @@ extern "C" size_t gfb_kde_sym_workspace_bytes(int B, int M) {
 }
 
 // kde(x) with y = x (down == 1), D = 4: symmetric evaluation, see kde4_sym_kernel.  cut_sigmas > 0 additionally sorts
-// the points along a Morton curve and skips tile pairs further apart than cut_sigmas * std (0 = evaluate every pair).
+// the points along a Hilbert curve and skips tile pairs further apart than cut_sigmas * std (0 = evaluate every pair).
 extern "C" int gfb_kde_sym_f32(const float* x, float* density, int B, int M, float std, float cut_sigmas,
                                void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
     GFB_CHECK_ARG(x && density && B > 0 && M > 0 && std > 0.f && cut_sigmas >= 0.f);

@@ -150,7 +150,7 @@ int gfb_kde_f32(const float* x, float* density, int B, int M, int D, int down, f
 /* Same operator for the configuration the reference uses on CUDA (down = 1, i.e. y = x; D = 4; model/network.py:405-408):
  * the kernel is symmetric, so only tile pairs (I, J >= I) are evaluated and every value is added to its row and its
  * column -- half the exponentials.  Sums meet in a 64-bit fixed-point accumulator (deterministic).
- *   cut_sigmas > 0: the points are first sorted along a Morton curve (the library's own top-k kernel) and tile pairs
+ *   cut_sigmas > 0: the points are first sorted along a Hilbert curve (the library's own top-k kernel) and tile pairs
  *   whose bounding boxes are further apart than cut_sigmas * std are skipped; every skipped term is below
  *   exp(-cut_sigmas^2 / 2) (2.3e-11 at 7: < 5e-7 of a density >= 1 for M = 20000).  0 evaluates every pair.
  *   workspace >= gfb_kde_sym_workspace_bytes(B, M) bytes, 256-byte aligned; zeroed by the call. */

@@ -284,7 +284,7 @@ def test_kde_symmetric_kernel(gf):
         x = synth.make_matches(synth.random_homography(cgen), m, gen, "cuda")
         ref = oracle.kde_def(x.cpu(), 0.1)
         full = gf.kde(x, 0.1, half=False, algo=KDE_FULL)
-        for cut in (None, 0.0, 5.0):      # default 7-sigma cut-off (Morton sort + block boxes), every pair, tighter cut
+        for cut in (None, 0.0, 5.0):      # default 7-sigma cut-off (Hilbert sort + block boxes), every pair, tighter cut
             a = gf.kde(x, 0.1, half=False, algo=KDE_SYMMETRIC, cut_sigmas=cut)
             _close(a, ref, rtol=1e-4, atol_rel=0)
             _close(a, full, rtol=2e-5 if cut != 5.0 else 1e-4, atol_rel=0)
