@@ -104,9 +104,11 @@ __global__ void __launch_bounds__(TK_THREADS, 1) topk_kernel(const float* __rest
     uint32_t* wi = wk + TK_THREADS * IPT;
     if (threadIdx.x == 0) { s_prefix = 0; s_mask = 0; s_remaining = k; }
 
-    // ---- radix select, most significant digits first (11 + 11 + 10 bits)
+    // ---- radix select, most significant digits first (11 + 11 + 10 bits); k == n (a full sort, e.g. the kde's
+    // space-filling-curve ordering) needs neither the select nor the compaction
     const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
-    for (int pass = 0; pass < 3; ++pass) {
+    const bool full = (long long)k == n;
+    for (int pass = 0; pass < (full ? 0 : 3); ++pass) {
         for (int i = threadIdx.x; i < 2048; i += TK_THREADS) hist[i] = 0;
         __syncthreads();
         const uint32_t prefix = s_prefix, mask = s_mask;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) topk_kernel(const float* __rest
 
     // ---- ordered compaction of the winners (index order) into scratch
     int base_sel = 0, base_eq = 0;
-    for (long long t0 = 0; t0 < n; t0 += (long long)TK_THREADS * 4) {
+    for (long long t0 = 0; t0 < (full ? 0 : n); t0 += (long long)TK_THREADS * 4) {
         const long long i0 = t0 + (long long)threadIdx.x * 4;
         uint32_t u[4];
         int eq = 0;
@@ -175,8 +177,13 @@ __global__ void __launch_bounds__(TK_THREADS, 1) topk_kernel(const float* __rest
 #pragma unroll
     for (int e = 0; e < IPT; ++e) {
         const int p = threadIdx.x * IPT + e;
-        sk[e] = p < k ? wk[p] : 0u;       // padding sorts last (every real key has its top bit set or is > 0)
-        sv[e] = p < k ? wi[p] : 0u;
+        if (full) {
+            sk[e] = p < k ? order_key(row[p]) : 0u;
+            sv[e] = p < k ? (uint32_t)p : 0u;
+        } else {
+            sk[e] = p < k ? wk[p] : 0u;   // padding sorts last (every real key has its top bit set or is > 0)
+            sv[e] = p < k ? wi[p] : 0u;
+        }
     }
     Sort(sort_tmp).SortDescending(sk, sv);
 #pragma unroll
