@@ -120,12 +120,14 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
             base = int(algo) & 15
             plain = _tc_eligible_modes(win_h, win_w, hs, ws, sample_mode, padding_mode)
             if (prepared is not None and level == 0 and num_level == 1 and plain and int(algo) == ALGO_AUTO
-                    and prepared.matches((B, c, h, w), f0, f1, r, G)):
+                    and B * kk * G * G < 2 ** 31 and prepared.matches((B, c, h, w), f0, f1, r, G)):
                 rc = lib.gfb_local_corr_tc2_run_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r, kk, 0,
                                                     ptr(prepared.wsbuf), prepared.nws, st)
                 check(rc, "local_correlation (tcgen05, prepared features)")
                 continue
-            if base == ALGO_TC2 or (int(algo) == ALGO_AUTO and plain and (r, c) in _TC2_SHAPES):
+            # (the tcgen05 kernel indexes its output with 32 bits; larger problems stay on the general entry)
+            if base == ALGO_TC2 or (int(algo) == ALGO_AUTO and plain and (r, c) in _TC2_SHAPES
+                                    and B * kk * num_level * G * G < 2 ** 31):
                 if not (plain and (r, c) in _TC2_SHAPES):
                     raise NotImplementedError("local_correlation: the TMA-fed tcgen05 kernel covers bilinear/zeros with "
                                               f"(r, C) in {sorted(_TC2_SHAPES)}, got r={r}, C={c}")
