@@ -195,6 +195,7 @@ __device__ void jacobi9_smallest(double* A /*81*/, double* V /*81*/, double* out
 }
 
 __global__ void __launch_bounds__(RF_THREADS) refit_kernel(HgParams p) {
+    extern __shared__ float s_w[];           // [N] weight of every point (0 = not an inlier), filled by the first pass
     __shared__ double sm_part[(RF_THREADS / 32) * 30];
     __shared__ double sm_red[32];
     __shared__ double sA[81], sV[81], sh[9], sH[9];
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(RF_THREADS) refit_kernel(HgParams p) {
     for (int i = threadIdx.x; i < p.N; i += RF_THREADS) {
         float4 q; to_pixels(p, __ldg(mb + i), q.x, q.y, q.z, q.w);
         const double w = weight_of(i, q);
+        s_w[i] = (float)w;                   // weights are floats (or 1): the round trip is exact
         if (mk) mk[i] = w > 0.0;
         a6[0] += w; a6[1] += (w > 0.0); a6[2] += w * q.x; a6[3] += w * q.y; a6[4] += w * q.z; a6[5] += w * q.w;
     }
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(RF_THREADS) refit_kernel(HgParams p) {
     double d4[4] = {0, 0, 0, 0};
     for (int i = threadIdx.x; i < p.N; i += RF_THREADS) {
         float4 q; to_pixels(p, __ldg(mb + i), q.x, q.y, q.z, q.w);
-        const double w = weight_of(i, q);
+        const double w = (double)s_w[i];
         d4[0] += w * fabs(q.x - cAx); d4[1] += w * fabs(q.y - cAy); d4[2] += w * fabs(q.z - cBx); d4[3] += w * fabs(q.w - cBy);
     }
     block_reduce<4>(d4, sm_part, sm_red);
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(RF_THREADS) refit_kernel(HgParams p) {
     for (int e = 0; e < 24; ++e) acc[e] = 0;
     for (int i = threadIdx.x; i < p.N; i += RF_THREADS) {
         float4 q; to_pixels(p, __ldg(mb + i), q.x, q.y, q.z, q.w);
-        const double w = weight_of(i, q);
+        const double w = (double)s_w[i];
         if (w == 0.0) continue;
         const double X = (q.x - cAx) * sAx, Y = (q.y - cAy) * sAy, x = (q.z - cBx) * sBx, y = (q.w - cBy) * sBy;
         const double u[6] = {X * X, X * Y, X, Y * Y, Y, 1.0};   // upper triangle of u u^T, u = (X, Y, 1)
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(RF_THREADS) refit_kernel(HgParams p) {
         for (int e = 0; e < 30; ++e) g[e] = 0;
         for (int i = threadIdx.x; i < p.N; i += RF_THREADS) {
             float4 q; to_pixels(p, __ldg(mb + i), q.x, q.y, q.z, q.w);
-            const double w = weight_of(i, q);
+            const double w = (double)s_w[i];
             if (w == 0.0) continue;
             const double X = q.x, Y = q.y;
             const double ww = 1.0 / (h[6] * X + h[7] * Y + 1.0);
@@ -435,7 +437,11 @@ extern "C" int gfb_homography_f32(const float* matches, const float* weights, in
         e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
-    refit_kernel<<<B, RF_THREADS, 0, st>>>(p);
+    const size_t rsmem = (size_t)N * sizeof(float);
+    if (rsmem > 200 * 1024) return GFB_EUNSUPPORTED;
+    cudaError_t e2 = cudaFuncSetAttribute(refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+    if (e2 != cudaSuccess) return (int)e2;
+    refit_kernel<<<B, RF_THREADS, rsmem, st>>>(p);
     GFB_LAUNCH_RESULT();
 }
 
