@@ -108,15 +108,27 @@ __global__ void __launch_bounds__(TK_THREADS, 1) topk_kernel(const float* __rest
     // space-filling-curve ordering) needs neither the select nor the compaction
     const int shifts[3] = {21, 10, 0}, nbits[3] = {11, 11, 10};
     const bool full = (long long)k == n;
+    const bool vec4 = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
     for (int pass = 0; pass < (full ? 0 : 3); ++pass) {
         for (int i = threadIdx.x; i < 2048; i += TK_THREADS) hist[i] = 0;
         __syncthreads();
         const uint32_t prefix = s_prefix, mask = s_mask;
         const int remaining = s_remaining;
         const int sh = shifts[pass], nb = 1 << nbits[pass];
-        for (long long i = threadIdx.x; i < n; i += TK_THREADS) {
-            const uint32_t u = order_key(row[i]);
-            if ((u & mask) == prefix) atomicAdd(&hist[(u >> sh) & (nb - 1)], 1);
+        if (vec4) {   // 16-byte loads: four keys per thread and iteration in flight
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+            for (long long i = threadIdx.x; i < n / 4; i += TK_THREADS) {
+                const float4 v = __ldg(row4 + i);
+                const uint32_t u[4] = {order_key(v.x), order_key(v.y), order_key(v.z), order_key(v.w)};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if ((u[e] & mask) == prefix) atomicAdd(&hist[(u[e] >> sh) & (nb - 1)], 1);
+            }
+        } else {
+            for (long long i = threadIdx.x; i < n; i += TK_THREADS) {
+                const uint32_t u = order_key(row[i]);
+                if ((u & mask) == prefix) atomicAdd(&hist[(u >> sh) & (nb - 1)], 1);
+            }
         }
         __syncthreads();
         // suffix sums over bins, highest bin first: thread t owns bins nb-1-4t .. nb-4-4t
