@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(KDE_THREADS) kde4_kernel(const float* __restri
 // transpose-reduce after every tile pair.  Partial sums meet in a 64-bit fixed-point accumulator (2^-40 units):
 // integer atomics are order-independent, so the density is deterministic although CTAs finish in any order.
 constexpr int KS_T = 128;
-constexpr int KS_JC = 16;
+constexpr int KS_JC = 32;
 constexpr int KS_PITCH = 16 * 9;
 constexpr float KS_FIX = 1099511627776.f;   // 2^40
 
@@ -163,13 +163,17 @@ __global__ void __launch_bounds__(256, 3) kde4_sym_kernel(const float* __restric
     if (jfirst >= nb) return;
     const int tid = threadIdx.x, ti = tid & 15, tj = tid >> 4;
     if (tid < 32) {
-        const int J = jfirst + tid;
-        bool keep = tid < KS_JC && J < nb;
-        if (keep && cut2 > 0.f && J != I)
-            keep = bb_dist2(bb + ((size_t)b * nb + I) * 8, bb + ((size_t)b * nb + J) * 8) <= cut2;
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) jl[__popc(m & ((1u << tid) - 1u))] = J;
-        if (tid == 0) jl[KS_JC] = __popc(m);
+        int cnt = 0;
+        for (int base = 0; base < KS_JC; base += 32) {
+            const int J = jfirst + base + tid;
+            bool keep = base + tid < KS_JC && J < nb;
+            if (keep && cut2 > 0.f && J != I)
+                keep = bb_dist2(bb + ((size_t)b * nb + I) * 8, bb + ((size_t)b * nb + J) * 8) <= cut2;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) jl[cnt + __popc(m & ((1u << tid) - 1u))] = J;
+            cnt += __popc(m);
+        }
+        if (tid == 0) jl[KS_JC] = cnt;
     }
     __syncthreads();
     const int nj = jl[KS_JC];
@@ -407,7 +411,7 @@ extern "C" int gfb_kde_sym_f32(const float* x, float* density, int B, int M, flo
     cudaError_t e = cudaMemsetAsync(acc, 0, n * 8, st);
     if (e != cudaSuccess) return (int)e;
     // the sort reuses the top-k kernel (k = n): it orders at most 20480 keys per row
-    const bool cut = cut_sigmas > 0.f && gfb_topk_workspace_bytes(B, M, M) > 0 && M <= 20480 && nb > KS_JC;
+    const bool cut = cut_sigmas > 0.f && gfb_topk_workspace_bytes(B, M, M) > 0 && M <= 20480 && nb > 16;
     const unsigned gs = (unsigned)min((size_t)148 * 8, (n + 255) / 256);
     if (cut) {
         kde_keys_kernel<<<gs, 256, 0, st>>>(reinterpret_cast<const float4*>(x), keys, n);
