@@ -39,6 +39,10 @@ __device__ __forceinline__ float2 unpack2(unsigned long long v) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
     return r;
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -300,6 +304,339 @@ static int launch_pt(const LcParams& p, cudaStream_t st) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TX * TY, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const int grid = (int)min(tiles, (long long)sms * per_sm);
     kern<<<grid, TX * TY, smem, st>>>(p, (int)tiles, tmap1, tmap0);
+    GFB_LAUNCH_RESULT();
+}
+
+// =====================================================================================================================
+// lc_rot_kernel: one point per thread, conflict-free window reads by rotating the visiting order (r = 2)
+// =====================================================================================================================
+// lc_pt_kernel sits on the shared-memory roof (ncu: 3.6 wavefronts per LDS.64 where 2 are ideal, plus two padding columns
+// per window row): neighbouring lattice points read windows that start ~1.75 px apart and on different image rows, so the
+// lanes of one load collide in the banks.  Here every lane visits the W x W cells of its window in a rotated order:
+// instruction (jj, ii) reads the one cell of the lane's window whose box row is == jj and whose box column is == ii
+// (mod W).  All lanes of a load then touch cells of ONE residue class; two different cells of a class are multiples of W
+// apart in x and / or y, and with a box pitch of 8 or 24 (mod 32) words they fall into different banks across the
+// footprint of a warp of 16 x 2 lattice points (equal cells broadcast).  Measured on the bench flows by simulation
+// (tools/sim/sim5.py): 1.003 wavefronts per LDS.32, against 1.88 per half-warp LDS.64 before -- exactly W*W loads per
+// point and channel, no padding columns.  The accumulators are un-rotated once per tile by a select network.
+//
+// The rest of the kernel is built around the two other limits the first kernel hit: (1) the L2 -> shared-memory fill:
+// the TMA box of a tile is the narrowest / shortest of 3 x 5 shapes that holds the tile's windows (16 x 16 points per
+// tile: 8.8 staged pixels per point in the median instead of 16); (2) barriers: a producer warp (geometry of the next
+// tile, tile descriptor, TMA issue) and eight consumer warps meet only through full / empty mbarriers, there is no
+// CTA-wide barrier in the main loop.
+namespace rot {
+constexpr int R = 2, W = 6, KW = 5, KK = 25;
+constexpr int TX = 16, TY = 16, NT = TX * TY, NCW = NT / 32;     // tile, consumer warps
+constexpr int NBW = 3, NBH = 5;
+__host__ __device__ constexpr int box_w(int i) { return 40 + 16 * i; }       // 40, 56, 72: all 8 or 24 (mod 32)
+__host__ __device__ constexpr int box_h(int i) { return 24 + 8 * i; }        // 24 .. 56
+constexpr int NTS = 3;                                                         // tile slots (descriptor + point geometry)
+struct Maps { CUtensorMap m[NBW][NBH]; };
+struct TileInfo { int tile, P, bh, flags; int X0, Y0, bwi, bhi; };
+struct Geom { int u, oy; float fx, fy; };                                     // u < 0: window misses the image
+}  // namespace rot
+
+// rotate a 6-vector: out[j] = v[(j + n) % 6], n in [0, 6)
+__device__ __forceinline__ void rot6(float (&v)[6], int n) {
+    float t[6];
+#pragma unroll
+    for (int s = 1; s <= 4; s <<= 1) {
+        const bool on = (n & s) != 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) t[j] = on ? v[(j + s) % 6] : v[j];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] = t[j];
+    }
+}
+
+template <int C, int NBUF, int MBW, int MBH>
+__global__ void __launch_bounds__(rot::NT + 32, 2)
+lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::Maps maps,
+              const __grid_constant__ CUtensorMap tmap0) {
+    using namespace rot;
+    constexpr int BOXMAX = box_w(MBW) * box_h(MBH);                            // floats of the largest box
+    constexpr int SLOT = BOXMAX + NT;                                          // ring slot: one channel of f1 box + f0 tile
+    static_assert((SLOT * 4) % 128 == 0 && (BOXMAX * 4) % 128 == 0 && C % 2 == 0 && NBUF % 2 == 0, "ring layout");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);                          // [NBUF][SLOT]: f1 box, then f0[NT]
+    Geom* geom = reinterpret_cast<Geom*>(ring + NBUF * SLOT);                  // [NTS][NT]
+    TileInfo* info = reinterpret_cast<TileInfo*>(geom + NTS * NT);             // [NTS]
+    uint64_t* full = reinterpret_cast<uint64_t*>(info + NTS);                  // [NBUF]
+    uint64_t* empty = full + NBUF;                                             // [NBUF]
+    uint64_t* tfull = empty + NBUF;                                            // [NTS] descriptor + geometry ready
+    uint64_t* tempty = tfull + NTS;                                            // [NTS]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = p.G;
+    const size_t gg = (size_t)G * G;
+    const int tiles_x = (G + TX - 1) / TX, tiles_y = (G + TY - 1) / TY;
+
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCW); }
+        for (int i = 0; i < NTS; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NCW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ================= producer warp: geometry one tile ahead, box choice, TMA issue =================
+        // raw flow of this lane's NT / 32 points, loaded two tiles ahead of the stage loop that needs the box
+        float rx[NT / 32], ry[NT / 32];
+        auto load_flow = [&](int tile) {
+            int t = tile;
+            const int tx = t % tiles_x; t /= tiles_x;
+            const int ty = t % tiles_y;
+            const int b = t / tiles_y;
+#pragma unroll
+            for (int k = 0; k < NT / 32; ++k) {
+                const int pi = lane + 32 * k;
+                const int gx = tx * TX + (pi % TX), gy = ty * TY + (pi / TX);
+                rx[k] = ry[k] = __int_as_float(0x7fc00000);   // NaN = no point
+                if (tile < ntiles && gx < G && gy < G) {
+                    const float* fl = p.flow + (size_t)b * 2 * gg + (size_t)gy * G + gx;
+                    rx[k] = __ldg(fl); ry[k] = __ldg(fl + gg);
+                }
+            }
+        };
+        // descriptor + geometry of `tile` into tile slot n % NTS (from rx / ry); returns the box of the tile
+        struct Box { int X0, Y0, bwi, bhi, none; };
+        auto prepare = [&](int tile, int n) {
+            Box bx;
+            const int slot = n % NTS;
+            mbar_wait(&tempty[slot], ((n / NTS) & 1) ^ 1);
+            if (tile >= ntiles) {                             // end marker
+                if (lane == 0) { info[slot].tile = -1; mbar_arrive(&tfull[slot]); }
+                bx.X0 = bx.Y0 = bx.bwi = bx.bhi = 0; bx.none = 1;
+                return bx;
+            }
+            PointGeom pg[NT / 32];
+            int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+#pragma unroll
+            for (int k = 0; k < NT / 32; ++k) {
+                PointGeom g;
+                g.xb = 0; g.yb = 0; g.fx = 0.f; g.fy = 0.f; g.live = false;
+                const float sx = unnormalize(rx[k], p.Ws), sy = unnormalize(ry[k], p.Hs);
+                if (fabsf(sx) < 1e6f && fabsf(sy) < 1e6f) {   // false for NaN (no point) too
+                    const float x0f = floorf(sx), y0f = floorf(sy);
+                    g.xb = (int)x0f - R; g.yb = (int)y0f - R;
+                    g.fx = sx - x0f; g.fy = sy - y0f;
+                    g.live = !(g.xb >= p.Ws || g.xb + W <= 0 || g.yb >= p.Hs || g.yb + W <= 0);
+                }
+                pg[k] = g;
+                if (g.live) {
+                    mnx = min(mnx, g.xb); mxx = max(mxx, g.xb);
+                    mny = min(mny, g.yb); mxy = max(mxy, g.yb);
+                }
+            }
+            mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+            bx.none = mnx == INT_MAX;
+            bx.X0 = bx.none ? 0 : (mnx & ~3); bx.Y0 = bx.none ? 0 : mny;      // 16-byte aligned innermost coordinate
+            const int ex = bx.none ? 0 : mxx + W - bx.X0, ey = bx.none ? 0 : mxy + W - bx.Y0;
+            bx.bwi = min(max((ex - box_w(0) + 15) / 16, 0), MBW);
+            bx.bhi = min(max((ey - box_h(0) + 7) / 8, 0), MBH);
+#pragma unroll
+            for (int k = 0; k < NT / 32; ++k) {
+                Geom gm;
+                gm.u = pg[k].live ? pg[k].xb - bx.X0 : -1;
+                gm.oy = pg[k].yb - bx.Y0;
+                gm.fx = pg[k].fx; gm.fy = pg[k].fy;
+                geom[slot * NT + lane + 32 * k] = gm;
+            }
+            if (lane == 0) {
+                TileInfo ti;
+                ti.tile = tile; ti.P = box_w(bx.bwi); ti.bh = box_h(bx.bhi); ti.flags = bx.none ? 1 : 0;
+                ti.X0 = bx.X0; ti.Y0 = bx.Y0; ti.bwi = bx.bwi; ti.bhi = bx.bhi;
+                info[slot] = ti;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tfull[slot]);
+            if (!bx.none && lane < C) {                       // pull the tile's boxes into L2 a whole tile ahead of their TMA loads
+                int t = tile;
+                const int tx = t % tiles_x; t /= tiles_x;
+                const int ty = t % tiles_y;
+                const int b = t / tiles_y;
+                tma_prefetch_3d(&maps.m[bx.bwi][bx.bhi], bx.X0, bx.Y0, b * C + lane);
+                tma_prefetch_3d(&tmap0, tx * TX, ty * TY, b * C + lane);
+            }
+            return bx;
+        };
+        uint32_t q = 0;                                       // ring stages issued
+        int tile = blockIdx.x;
+        load_flow(tile);
+        Box cur = prepare(tile, 0);
+        load_flow(tile + gridDim.x);
+        for (int n = 0; tile < ntiles; ++n, tile += gridDim.x) {
+            const Box nxt = prepare(tile + gridDim.x, n + 1); // consumers find the next tile ready when they get there
+            load_flow(tile + 2 * gridDim.x);                  // in flight during the stage loop below
+            if (lane == 0 && !cur.none) {
+                int t = tile;
+                const int tx = t % tiles_x; t /= tiles_x;
+                const int ty = t % tiles_y;
+                const int b = t / tiles_y;
+                const CUtensorMap* tm = &maps.m[cur.bwi][cur.bhi];
+                const uint32_t bytes = (uint32_t)((box_w(cur.bwi) * box_h(cur.bhi) + NT) * sizeof(float));
+                for (int c = 0; c < C; ++c, ++q) {
+                    const uint32_t s = q % NBUF;
+                    mbar_wait(&empty[s], ((q / NBUF) & 1) ^ 1);
+                    if (p.debug & 2) { mbar_arrive(&full[s]); continue; }
+                    mbar_expect_tx(&full[s], bytes);
+                    tma_load_3d(ring + s * SLOT, tm, &full[s], cur.X0, cur.Y0, b * C + c);
+                    tma_load_3d(ring + s * SLOT + BOXMAX, &tmap0, &full[s], tx * TX, ty * TY, b * C + c);
+                }
+            }
+            __syncwarp();
+            cur = nxt;
+        }
+        return;
+    }
+
+    // ================= consumer warps: thread = lattice point (warp = 16 x 2 points) =================
+    const unsigned char* ring_b = reinterpret_cast<const unsigned char*>(ring);
+    uint32_t q = 0;
+    for (int n = 0; ; ++n) {
+        const int slot = n % NTS;
+        mbar_wait(&tfull[slot], (n / NTS) & 1);
+        const TileInfo ti = info[slot];
+        if (ti.tile < 0) break;
+        const Geom gm = geom[slot * NT + tid];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[slot]);            // descriptor and geometry are in registers now
+        int t = ti.tile;
+        const int tx = t % tiles_x; t /= tiles_x;
+        const int ty = t % tiles_y;
+        const int b = t / tiles_y;
+        const int gx = tx * TX + (tid % TX), gy = ty * TY + (tid / TX);
+        const bool valid = gx < G && gy < G;
+        const bool live = gm.u >= 0;
+        const bool fit = live && gm.u + W <= ti.P && gm.oy + W <= ti.bh;
+        const int u = fit ? gm.u : 0, oy = fit ? gm.oy : 0;
+        const int m = u % W, nn = oy % W;
+        // instruction (jj, ii) reads box row oy - nn + jj (+ W if jj < nn), box column u - m + ii (+ W if ii < m)
+        int rowb[W], colb[W];                                 // byte offsets
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            rowb[k] = (oy - nn + k + (k < nn ? W : 0)) * ti.P * 4;
+            colb[k] = (u - m + k + (k < m ? W : 0)) * 4;
+        }
+        unsigned long long acc[W][W / 2];
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+#pragma unroll
+            for (int h = 0; h < W / 2; ++h) acc[j][h] = 0ull;
+        if (!(ti.flags & 1)) {
+#pragma unroll 1
+            for (int c = 0; c < C; c += 2, q += 2) {          // two channels per step: ring slots s, s + 1 (NBUF even)
+                const uint32_t s = q % NBUF;
+                const uint32_t par = (q / NBUF) & 1;
+                mbar_wait(&full[s], par);
+                mbar_wait(&full[s + 1], par);
+                if (fit && !(p.debug & 1)) {
+                    const unsigned char* sb = ring_b + s * (SLOT * 4);
+                    const float fa = *reinterpret_cast<const float*>(sb + (BOXMAX + tid) * 4);
+                    const float fb = *reinterpret_cast<const float*>(sb + (BOXMAX + tid) * 4 + SLOT * 4);
+                    const unsigned long long f0a = pack2(fa, fa), f0b = pack2(fb, fb);
+#pragma unroll
+                    for (int jj = 0; jj < W; ++jj) {
+                        const unsigned char* rb = sb + rowb[jj];
+#pragma unroll
+                        for (int h = 0; h < W / 2; ++h) {
+                            const unsigned char* a0 = rb + colb[2 * h];
+                            const unsigned char* a1 = rb + colb[2 * h + 1];
+                            const float v0 = *reinterpret_cast<const float*>(a0), v1 = *reinterpret_cast<const float*>(a1);
+                            const float w0 = *reinterpret_cast<const float*>(a0 + SLOT * 4);
+                            const float w1 = *reinterpret_cast<const float*>(a1 + SLOT * 4);
+                            ffma2(acc[jj][h], pack2(v0, v1), f0a);
+                            ffma2(acc[jj][h], pack2(w0, w1), f0b);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&empty[s]); mbar_arrive(&empty[s + 1]); }
+            }
+        }
+
+        float* outp = p.out + ((size_t)b * p.k_total + p.k_offset) * gg + (size_t)gy * G + gx;
+        if (fit) {
+            // un-rotate: D[j][i] = acc[(j + nn) % W][(i + m) % W]
+            float D[W][W];
+#pragma unroll
+            for (int jj = 0; jj < W; ++jj)
+#pragma unroll
+                for (int h = 0; h < W / 2; ++h) {
+                    const float2 v = unpack2(acc[jj][h]);
+                    D[jj][2 * h] = v.x; D[jj][2 * h + 1] = v.y;
+                }
+#pragma unroll
+            for (int jj = 0; jj < W; ++jj) rot6(D[jj], m);
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                float col[W];
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) col[jj] = D[jj][i];
+                rot6(col, nn);
+#pragma unroll
+                for (int jj = 0; jj < W; ++jj) D[jj][i] = col[jj];
+            }
+            const float a1 = gm.fx, a0 = 1.f - gm.fx;
+            const float wy1 = gm.fy * p.inv_sqrt_c, wy0 = (1.f - gm.fy) * p.inv_sqrt_c;
+            float hprev[KW];
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+#pragma unroll
+                for (int i = 0; i < KW; ++i) {
+                    const float h = a0 * D[j][i] + a1 * D[j][i + 1];
+                    if (j >= 1) st_stream(outp + (size_t)((j - 1) * KW + i) * gg, wy0 * hprev[i] + wy1 * h);
+                    hprev[i] = h;
+                }
+        } else if (valid) {
+            if (!live) {
+                for (int k = 0; k < KK; ++k) st_stream(outp + (size_t)k * gg, 0.f);
+            } else {
+                atomicAdd(&g_v2_stats[0], 1ull);
+                PointGeom pg;
+                pg.xb = gm.u + ti.X0; pg.yb = gm.oy + ti.Y0; pg.fx = gm.fx; pg.fy = gm.fy; pg.live = true;
+                lc_point_global<R>(p, b, gy, gx, pg, outp);
+            }
+        }
+    }
+}
+
+template <int C, int NBUF, int MBW = rot::NBW - 1, int MBH = rot::NBH - 1>
+static int launch_rot(const LcParams& p, cudaStream_t st) {
+    using namespace rot;
+    constexpr int SLOT = box_w(MBW) * box_h(MBH) + NT;
+    constexpr size_t smem = (size_t)NBUF * SLOT * sizeof(float) + NTS * NT * sizeof(Geom) + NTS * sizeof(TileInfo) +
+                            (2 * NBUF + 2 * NTS) * sizeof(uint64_t) + 128;
+    const int G = p.G;
+    if (G % 4 != 0) return GFB_EUNSUPPORTED;              // 16-byte global strides of the f0 tensor map
+    Maps maps;
+    CUtensorMap tmap0;
+    for (int i = 0; i < NBW; ++i)
+        for (int j = 0; j < NBH; ++j) {
+            uint64_t dims[3] = {(uint64_t)p.Ws, (uint64_t)p.Hs, (uint64_t)p.B * p.C};
+            uint64_t strides[2] = {(uint64_t)p.pitch * 4, (uint64_t)p.Hs * p.pitch * 4};
+            uint32_t box[3] = {(uint32_t)box_w(i), (uint32_t)box_h(j), 1u};
+            int rc = gfb_encode_tmap_f32(&maps.m[i][j], p.f1, 3, dims, strides, box, 0);
+            if (rc != GFB_OK) return rc;
+        }
+    {
+        uint64_t dims[3] = {(uint64_t)G, (uint64_t)G, (uint64_t)p.B * p.C};
+        uint64_t strides[2] = {(uint64_t)G * 4, (uint64_t)G * G * 4};
+        uint32_t box[3] = {(uint32_t)TX, (uint32_t)TY, 1u};
+        int rc = gfb_encode_tmap_f32(&tmap0, p.f0, 3, dims, strides, box, 0);
+        if (rc != GFB_OK) return rc;
+    }
+    auto kern = lc_rot_kernel<C, NBUF, MBW, MBH>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long tiles = (long long)p.B * ((G + TY - 1) / TY) * ((G + TX - 1) / TX);
+    if (tiles > 0x7fffffffLL) return GFB_EUNSUPPORTED;
+    int dev = 0, sms = 148, per_sm = 1;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT + 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int grid = (int)min(tiles, (long long)sms * per_sm);
+    kern<<<grid, NT + 32, smem, st>>>(p, (int)tiles, maps, tmap0);
     GFB_LAUNCH_RESULT();
 }
 
@@ -939,12 +1276,18 @@ extern "C" int gfb_local_corr_pt_f32(const float* f0, const float* f1, const flo
     if (rc != GFB_OK) return rc;
     if (p.pitch % 4 != 0 || !gfb_aligned(f1, 16)) return GFB_EALIGN;
     if ((size_t)B * C >= (1ull << 31)) return GFB_EUNSUPPORTED;
+    p.debug = tune >> 8; tune &= 255;
     cudaStream_t st = gfb_cu(stream);
     const float s = (float)Ws / (float)G;
     if (!gfb_aligned(f0, 16)) return GFB_EALIGN;
     // box = tile span x (1.3 magnification) + rotation shear + window + alignment, rounded up to a row pitch of 0 mod 32
     // floats: the 16 lanes of a half-warp then hit distinct banks whatever rows their windows start on
     if (r == 2 && C == 16) {
+        if (tune == 32) return lcv2::launch_rot<16, 4>(p, st);
+        if (tune == 33) return lcv2::launch_rot<16, 6>(p, st);
+        if (tune == 34) return lcv2::launch_rot<16, 4, 1, 2>(p, st);
+        if (tune == 35) return lcv2::launch_rot<16, 8, 1, 2>(p, st);
+        if (tune == 36) return lcv2::launch_rot<16, 10, 1, 2>(p, st);
         if (tune == 1 || (tune == 0 && s <= 1.2f)) return lcv2::launch_pt<2, 16, 16, 8, 64, 24, 2, 3>(p, st);
         if (tune == 2 || (tune == 0 && s <= 2.0f)) return lcv2::launch_pt<2, 16, 16, 8, 64, 32, 2, 3>(p, st);
         if (tune == 4) return lcv2::launch_pt<2, 16, 16, 8, 56, 32, 4, 2>(p, st);

@@ -48,8 +48,16 @@ class PreparedFeatures:
         self.size, self.f0, self.f1, self.r, self.G, self.wsbuf, self.nws = size, f0, f1, r, G, wsbuf, nws
 
     def matches(self, size, f0, f1, r, G):
-        return (self.size == tuple(size) and self.r == r and self.G == G and self.f0.data_ptr() == f0.data_ptr()
-                and self.f1.data_ptr() == f1.data_ptr() and self.f0._version == f0._version and self.f1._version == f1._version)
+        """Same tensors as at prepare time?  The handle keeps f0 / f1 alive, so equal (pointer, shape, stride) means the
+        same storage; the version counter catches in-place writes where autograd tracks one (inference tensors --
+        ``GFNet.match`` runs under ``torch.inference_mode``, model/network.py:285 -- have none)."""
+        def same(a, b):
+            if a.data_ptr() != b.data_ptr() or a.shape != b.shape or a.stride() != b.stride():
+                return False
+            if a.is_inference() or b.is_inference():
+                return True
+            return a._version == b._version
+        return self.size == tuple(size) and self.r == r and self.G == G and same(self.f0, f0) and same(self.f1, f1)
 
 
 def local_correlation_prepare(featuremap_size, feature0, feature1, local_radius, num_grid):

@@ -50,8 +50,7 @@ int main() {
     auto enc = reinterpret_cast<CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill)>(fn);
-    const int shapes[][3] = {{248, 1, 16}, {224, 1, 16}, {128, 1, 16}, {64, 1, 16}, {248, 2, 16}, {128, 4, 16}, {64, 8, 16}, {32, 16, 16},
-                             {248, 1, 64}, {128, 1, 64}, {64, 4, 16}, {256, 4, 4}, {224, 16, 1}};
+    const int shapes[][3] = {{64, 32, 2}, {96, 36, 1}, {40, 40, 1}, {56, 40, 1}, {72, 40, 1}, {56, 32, 1}, {56, 64, 1}, {56, 8, 1}, {56, 40, 2}, {56, 20, 2}, {128, 32, 1}, {224, 16, 1}, {32, 40, 1}};
     for (auto& sh : shapes) {
         const int bw = sh[0], bh = sh[1], bc = sh[2];
         CUtensorMap tm;
