@@ -331,10 +331,10 @@ constexpr int TX = 16, TY = 16, NT = TX * TY, NCW = NT / 32;     // tile, consum
 constexpr int NBW = 3, NBH = 5;
 __host__ __device__ constexpr int box_w(int i) { return 40 + 16 * i; }       // 40, 56, 72: all 8 or 24 (mod 32)
 __host__ __device__ constexpr int box_h(int i) { return 24 + 8 * i; }        // 24 .. 56
-constexpr int NTS = 3;                                                         // tile slots (descriptor + point geometry)
+constexpr int NTS = 3;                                                         // tile slots (bounding box + descriptor)
 struct Maps { CUtensorMap m[NBW][NBH]; };
-struct TileInfo { int tile, P, bh, flags; int X0, Y0, bwi, bhi; };
-struct Geom { int u, oy; float fx, fy; };                                     // u < 0: window misses the image
+struct TileInfo { int P, bh, X0, Y0; };                                       // P = 0: no window of the tile meets the image
+struct BBox { int mnx, mny, mxx, mxy; };
 }  // namespace rot
 
 // rotate a 6-vector: out[j] = v[(j + n) % 6], n in [0, 6)
@@ -350,6 +350,11 @@ __device__ __forceinline__ void rot6(float (&v)[6], int n) {
     }
 }
 
+// Roles.  Consumer warps (thread = lattice point, warp = 16 x 2 points): at the start of tile k they turn the flow of
+// their point of tile k+1 (loaded one tile earlier) into window origin + fractions, reduce the tile's bounding box into
+// shared memory and signal `gready`; then they load the flow of tile k+2, wait for the descriptor of tile k and run its
+// channels.  Producer warp (one lane): waits for `gready` of a tile, picks the TMA box, publishes the descriptor
+// (`tfull`) and streams the channels through the ring (each stage = one channel of the f1 box + the 16 x 16 f0 tile).
 template <int C, int NBUF, int MBW, int MBH>
 __global__ void __launch_bounds__(rot::NT + 32, 2)
 lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::Maps maps,
@@ -360,12 +365,12 @@ lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::M
     static_assert((SLOT * 4) % 128 == 0 && (BOXMAX * 4) % 128 == 0 && C % 2 == 0 && NBUF % 2 == 0, "ring layout");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ring = reinterpret_cast<float*>(smem_raw);                          // [NBUF][SLOT]: f1 box, then f0[NT]
-    Geom* geom = reinterpret_cast<Geom*>(ring + NBUF * SLOT);                  // [NTS][NT]
-    TileInfo* info = reinterpret_cast<TileInfo*>(geom + NTS * NT);             // [NTS]
-    uint64_t* full = reinterpret_cast<uint64_t*>(info + NTS);                  // [NBUF]
+    TileInfo* info = reinterpret_cast<TileInfo*>(ring + NBUF * SLOT);          // [NTS]
+    BBox* bbox = reinterpret_cast<BBox*>(info + NTS);                          // [NTS]
+    uint64_t* full = reinterpret_cast<uint64_t*>(bbox + NTS);                  // [NBUF]
     uint64_t* empty = full + NBUF;                                             // [NBUF]
-    uint64_t* tfull = empty + NBUF;                                            // [NTS] descriptor + geometry ready
-    uint64_t* tempty = tfull + NTS;                                            // [NTS]
+    uint64_t* gready = empty + NBUF;                                           // [NTS] bounding box of the tile complete
+    uint64_t* tfull = gready + NTS;                                            // [NTS] descriptor published
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = p.G;
@@ -374,143 +379,137 @@ lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::M
 
     if (tid == 0) {
         for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCW); }
-        for (int i = 0; i < NTS; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NCW); }
+        for (int i = 0; i < NTS; ++i) {
+            mbar_init(&gready[i], NCW); mbar_init(&tfull[i], 1);
+            bbox[i].mnx = INT_MAX; bbox[i].mny = INT_MAX; bbox[i].mxx = INT_MIN; bbox[i].mxy = INT_MIN;
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
     if (warp == NCW) {
-        // ================= producer warp: geometry one tile ahead, box choice, TMA issue =================
-        // raw flow of this lane's NT / 32 points, loaded two tiles ahead of the stage loop that needs the box
-        float rx[NT / 32], ry[NT / 32];
-        auto load_flow = [&](int tile) {
-            int t = tile;
-            const int tx = t % tiles_x; t /= tiles_x;
-            const int ty = t % tiles_y;
-            const int b = t / tiles_y;
-#pragma unroll
-            for (int k = 0; k < NT / 32; ++k) {
-                const int pi = lane + 32 * k;
-                const int gx = tx * TX + (pi % TX), gy = ty * TY + (pi / TX);
-                rx[k] = ry[k] = __int_as_float(0x7fc00000);   // NaN = no point
-                if (tile < ntiles && gx < G && gy < G) {
-                    const float* fl = p.flow + (size_t)b * 2 * gg + (size_t)gy * G + gx;
-                    rx[k] = __ldg(fl); ry[k] = __ldg(fl + gg);
-                }
-            }
-        };
-        // descriptor + geometry of `tile` into tile slot n % NTS (from rx / ry); returns the box of the tile
-        struct Box { int X0, Y0, bwi, bhi, none; };
-        auto prepare = [&](int tile, int n) {
-            Box bx;
-            const int slot = n % NTS;
-            mbar_wait(&tempty[slot], ((n / NTS) & 1) ^ 1);
-            if (tile >= ntiles) {                             // end marker
-                if (lane == 0) { info[slot].tile = -1; mbar_arrive(&tfull[slot]); }
-                bx.X0 = bx.Y0 = bx.bwi = bx.bhi = 0; bx.none = 1;
-                return bx;
-            }
-            PointGeom pg[NT / 32];
-            int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
-#pragma unroll
-            for (int k = 0; k < NT / 32; ++k) {
-                PointGeom g;
-                g.xb = 0; g.yb = 0; g.fx = 0.f; g.fy = 0.f; g.live = false;
-                const float sx = unnormalize(rx[k], p.Ws), sy = unnormalize(ry[k], p.Hs);
-                if (fabsf(sx) < 1e6f && fabsf(sy) < 1e6f) {   // false for NaN (no point) too
-                    const float x0f = floorf(sx), y0f = floorf(sy);
-                    g.xb = (int)x0f - R; g.yb = (int)y0f - R;
-                    g.fx = sx - x0f; g.fy = sy - y0f;
-                    g.live = !(g.xb >= p.Ws || g.xb + W <= 0 || g.yb >= p.Hs || g.yb + W <= 0);
-                }
-                pg[k] = g;
-                if (g.live) {
-                    mnx = min(mnx, g.xb); mxx = max(mxx, g.xb);
-                    mny = min(mny, g.yb); mxy = max(mxy, g.yb);
-                }
-            }
-            mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
-            bx.none = mnx == INT_MAX;
-            bx.X0 = bx.none ? 0 : (mnx & ~3); bx.Y0 = bx.none ? 0 : mny;      // 16-byte aligned innermost coordinate
-            const int ex = bx.none ? 0 : mxx + W - bx.X0, ey = bx.none ? 0 : mxy + W - bx.Y0;
-            bx.bwi = min(max((ex - box_w(0) + 15) / 16, 0), MBW);
-            bx.bhi = min(max((ey - box_h(0) + 7) / 8, 0), MBH);
-#pragma unroll
-            for (int k = 0; k < NT / 32; ++k) {
-                Geom gm;
-                gm.u = pg[k].live ? pg[k].xb - bx.X0 : -1;
-                gm.oy = pg[k].yb - bx.Y0;
-                gm.fx = pg[k].fx; gm.fy = pg[k].fy;
-                geom[slot * NT + lane + 32 * k] = gm;
-            }
-            if (lane == 0) {
+        // ================= producer =================
+        if (lane == 0) {
+            uint32_t q = 0;                                   // ring stages issued
+            long long d_we = 0, d_g = 0, d_tot = clock64();
+            int n = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
+                const int slot = n % NTS;
+                const long long c0 = clock64();
+                mbar_wait(&gready[slot], (n / NTS) & 1);
+                d_g += clock64() - c0;
+                const BBox bb = bbox[slot];
+                bbox[slot].mnx = INT_MAX; bbox[slot].mny = INT_MAX; bbox[slot].mxx = INT_MIN; bbox[slot].mxy = INT_MIN;
+                const bool none = bb.mnx == INT_MAX;
+                const int X0 = none ? 0 : (bb.mnx & ~3), Y0 = none ? 0 : bb.mny;    // 16-byte aligned innermost coordinate
+                const int ex = none ? 0 : bb.mxx + W - X0, ey = none ? 0 : bb.mxy + W - Y0;
+                const int bwi = min(max((ex - box_w(0) + 15) / 16, 0), MBW);
+                const int bhi = min(max((ey - box_h(0) + 7) / 8, 0), MBH);
                 TileInfo ti;
-                ti.tile = tile; ti.P = box_w(bx.bwi); ti.bh = box_h(bx.bhi); ti.flags = bx.none ? 1 : 0;
-                ti.X0 = bx.X0; ti.Y0 = bx.Y0; ti.bwi = bx.bwi; ti.bhi = bx.bhi;
+                ti.P = none ? 0 : box_w(bwi); ti.bh = box_h(bhi); ti.X0 = X0; ti.Y0 = Y0;
                 info[slot] = ti;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tfull[slot]);
-            if (!bx.none && lane < C) {                       // pull the tile's boxes into L2 a whole tile ahead of their TMA loads
+                mbar_arrive(&tfull[slot]);
+                if (none) continue;
                 int t = tile;
                 const int tx = t % tiles_x; t /= tiles_x;
                 const int ty = t % tiles_y;
                 const int b = t / tiles_y;
-                tma_prefetch_3d(&maps.m[bx.bwi][bx.bhi], bx.X0, bx.Y0, b * C + lane);
-                tma_prefetch_3d(&tmap0, tx * TX, ty * TY, b * C + lane);
-            }
-            return bx;
-        };
-        uint32_t q = 0;                                       // ring stages issued
-        int tile = blockIdx.x;
-        load_flow(tile);
-        Box cur = prepare(tile, 0);
-        load_flow(tile + gridDim.x);
-        for (int n = 0; tile < ntiles; ++n, tile += gridDim.x) {
-            const Box nxt = prepare(tile + gridDim.x, n + 1); // consumers find the next tile ready when they get there
-            load_flow(tile + 2 * gridDim.x);                  // in flight during the stage loop below
-            if (lane == 0 && !cur.none) {
-                int t = tile;
-                const int tx = t % tiles_x; t /= tiles_x;
-                const int ty = t % tiles_y;
-                const int b = t / tiles_y;
-                const CUtensorMap* tm = &maps.m[cur.bwi][cur.bhi];
-                const uint32_t bytes = (uint32_t)((box_w(cur.bwi) * box_h(cur.bhi) + NT) * sizeof(float));
+                const CUtensorMap* tm = &maps.m[bwi][bhi];
+                const uint32_t bytes = (uint32_t)((box_w(bwi) * box_h(bhi) + NT) * sizeof(float));
                 for (int c = 0; c < C; ++c, ++q) {
                     const uint32_t s = q % NBUF;
+                    const long long w0 = clock64();
                     mbar_wait(&empty[s], ((q / NBUF) & 1) ^ 1);
+                    d_we += clock64() - w0;
                     if (p.debug & 2) { mbar_arrive(&full[s]); continue; }
                     mbar_expect_tx(&full[s], bytes);
-                    tma_load_3d(ring + s * SLOT, tm, &full[s], cur.X0, cur.Y0, b * C + c);
+                    tma_load_3d(ring + s * SLOT, tm, &full[s], X0, Y0, b * C + c);
                     tma_load_3d(ring + s * SLOT + BOXMAX, &tmap0, &full[s], tx * TX, ty * TY, b * C + c);
                 }
             }
-            __syncwarp();
-            cur = nxt;
+            if (p.debug & 4) {
+                atomicAdd(&g_v2_stats[4], (unsigned long long)d_we);
+                atomicAdd(&g_v2_stats[5], (unsigned long long)d_g);
+                atomicAdd(&g_v2_stats[7], (unsigned long long)(clock64() - d_tot));
+            }
         }
         return;
     }
 
-    // ================= consumer warps: thread = lattice point (warp = 16 x 2 points) =================
+    // ================= consumer warps =================
+    // tile coordinates (b, ty, tx) advance by gridDim.x tiles per step: mixed-radix increments instead of divisions
+    struct TileCoord { int tx, ty, b; };
+    auto coord_of = [&](int tile) {
+        TileCoord c;
+        int t = tile;
+        c.tx = t % tiles_x; t /= tiles_x;
+        c.ty = t % tiles_y;
+        c.b = t / tiles_y;
+        return c;
+    };
+    const TileCoord step = coord_of((int)gridDim.x);
+    auto advance = [&](TileCoord& c) {
+        c.tx += step.tx; c.ty += step.ty; c.b += step.b;
+        if (c.tx >= tiles_x) { c.tx -= tiles_x; ++c.ty; }
+        if (c.ty >= tiles_y) { c.ty -= tiles_y; ++c.b; }
+    };
+    const int px = tid % TX, py = tid / TX;
+    // raw flow of this thread's point of a tile (NaN = no point); volatile so that the loads stay where they are issued
+    auto load_flow = [&](int tile, const TileCoord& c, float& rx, float& ry) {
+        rx = ry = __int_as_float(0x7fc00000);
+        const int gx = c.tx * TX + px, gy = c.ty * TY + py;
+        if (tile < ntiles && gx < G && gy < G) {
+            const float* fl = p.flow + (size_t)c.b * 2 * gg + (size_t)gy * G + gx;
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(rx) : "l"(fl));
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(ry) : "l"(fl + gg));
+        }
+    };
+    // flow -> geometry; contributes the window origin to the bounding box of tile slot `slot`
+    auto make_geom = [&](float rx, float ry, int slot) {
+        PointGeom g;
+        g.xb = 0; g.yb = 0; g.fx = 0.f; g.fy = 0.f; g.live = false;
+        const float sx = unnormalize(rx, p.Ws), sy = unnormalize(ry, p.Hs);
+        if (fabsf(sx) < 1e6f && fabsf(sy) < 1e6f) {           // false for NaN (no point) too
+            const float x0f = floorf(sx), y0f = floorf(sy);
+            g.xb = (int)x0f - R; g.yb = (int)y0f - R;
+            g.fx = sx - x0f; g.fy = sy - y0f;
+            g.live = !(g.xb >= p.Ws || g.xb + W <= 0 || g.yb >= p.Hs || g.yb + W <= 0);
+        }
+        const int mnx = warp_min(g.live ? g.xb : INT_MAX), mny = warp_min(g.live ? g.yb : INT_MAX);
+        const int mxx = warp_max(g.live ? g.xb : INT_MIN), mxy = warp_max(g.live ? g.yb : INT_MIN);
+        if (lane == 0) {
+            if (mnx != INT_MAX) {
+                atomicMin(&bbox[slot].mnx, mnx); atomicMin(&bbox[slot].mny, mny);
+                atomicMax(&bbox[slot].mxx, mxx); atomicMax(&bbox[slot].mxy, mxy);
+            }
+            mbar_arrive(&gready[slot]);                       // release: the atomics above are visible to the producer
+        }
+        return g;
+    };
+
     const unsigned char* ring_b = reinterpret_cast<const unsigned char*>(ring);
     uint32_t q = 0;
-    for (int n = 0; ; ++n) {
+    float rx, ry;
+    TileCoord tc = coord_of((int)blockIdx.x), tc2 = tc;   // this tile, the tile whose flow is loaded next
+    load_flow(blockIdx.x, tc2, rx, ry);
+    PointGeom g_nxt = make_geom(rx, ry, 0);
+    advance(tc2);
+    load_flow(blockIdx.x + gridDim.x, tc2, rx, ry);
+    int n = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n, advance(tc)) {
         const int slot = n % NTS;
+        const PointGeom gm = g_nxt;
+        if (tile + gridDim.x < ntiles) g_nxt = make_geom(rx, ry, (n + 1) % NTS);     // bounding box of the next tile
+        advance(tc2);
+        load_flow(tile + 2 * gridDim.x, tc2, rx, ry);
         mbar_wait(&tfull[slot], (n / NTS) & 1);
         const TileInfo ti = info[slot];
-        if (ti.tile < 0) break;
-        const Geom gm = geom[slot * NT + tid];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[slot]);            // descriptor and geometry are in registers now
-        int t = ti.tile;
-        const int tx = t % tiles_x; t /= tiles_x;
-        const int ty = t % tiles_y;
-        const int b = t / tiles_y;
-        const int gx = tx * TX + (tid % TX), gy = ty * TY + (tid / TX);
+        const int b = tc.b, gx = tc.tx * TX + px, gy = tc.ty * TY + py;
         const bool valid = gx < G && gy < G;
-        const bool live = gm.u >= 0;
-        const bool fit = live && gm.u + W <= ti.P && gm.oy + W <= ti.bh;
-        const int u = fit ? gm.u : 0, oy = fit ? gm.oy : 0;
+        const bool live = gm.live;
+        const int gu = gm.xb - ti.X0, goy = gm.yb - ti.Y0;
+        const bool fit = live && gu + W <= ti.P && goy + W <= ti.bh;
+        const int u = fit ? gu : 0, oy = fit ? goy : 0;
         const int m = u % W, nn = oy % W;
         // instruction (jj, ii) reads box row oy - nn + jj (+ W if jj < nn), box column u - m + ii (+ W if ii < m)
         int rowb[W], colb[W];                                 // byte offsets
@@ -524,7 +523,7 @@ lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::M
         for (int j = 0; j < W; ++j)
 #pragma unroll
             for (int h = 0; h < W / 2; ++h) acc[j][h] = 0ull;
-        if (!(ti.flags & 1)) {
+        if (ti.P != 0) {
 #pragma unroll 1
             for (int c = 0; c < C; c += 2, q += 2) {          // two channels per step: ring slots s, s + 1 (NBUF even)
                 const uint32_t s = q % NBUF;
@@ -594,9 +593,7 @@ lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::M
                 for (int k = 0; k < KK; ++k) st_stream(outp + (size_t)k * gg, 0.f);
             } else {
                 atomicAdd(&g_v2_stats[0], 1ull);
-                PointGeom pg;
-                pg.xb = gm.u + ti.X0; pg.yb = gm.oy + ti.Y0; pg.fx = gm.fx; pg.fy = gm.fy; pg.live = true;
-                lc_point_global<R>(p, b, gy, gx, pg, outp);
+                lc_point_global<R>(p, b, gy, gx, gm, outp);
             }
         }
     }
@@ -606,7 +603,7 @@ template <int C, int NBUF, int MBW = rot::NBW - 1, int MBH = rot::NBH - 1>
 static int launch_rot(const LcParams& p, cudaStream_t st) {
     using namespace rot;
     constexpr int SLOT = box_w(MBW) * box_h(MBH) + NT;
-    constexpr size_t smem = (size_t)NBUF * SLOT * sizeof(float) + NTS * NT * sizeof(Geom) + NTS * sizeof(TileInfo) +
+    constexpr size_t smem = (size_t)NBUF * SLOT * sizeof(float) + NTS * (sizeof(TileInfo) + sizeof(BBox)) +
                             (2 * NBUF + 2 * NTS) * sizeof(uint64_t) + 128;
     const int G = p.G;
     if (G % 4 != 0) return GFB_EUNSUPPORTED;              // 16-byte global strides of the f0 tensor map
@@ -1283,13 +1280,10 @@ extern "C" int gfb_local_corr_pt_f32(const float* f0, const float* f1, const flo
     // box = tile span x (1.3 magnification) + rotation shear + window + alignment, rounded up to a row pitch of 0 mod 32
     // floats: the 16 lanes of a half-warp then hit distinct banks whatever rows their windows start on
     if (r == 2 && C == 16) {
+        if (tune == 0 || tune == 33) return lcv2::launch_rot<16, 6>(p, st);      // default: rotated-order kernel
         if (tune == 32) return lcv2::launch_rot<16, 4>(p, st);
-        if (tune == 33) return lcv2::launch_rot<16, 6>(p, st);
-        if (tune == 34) return lcv2::launch_rot<16, 4, 1, 2>(p, st);
-        if (tune == 35) return lcv2::launch_rot<16, 8, 1, 2>(p, st);
-        if (tune == 36) return lcv2::launch_rot<16, 10, 1, 2>(p, st);
-        if (tune == 1 || (tune == 0 && s <= 1.2f)) return lcv2::launch_pt<2, 16, 16, 8, 64, 24, 2, 3>(p, st);
-        if (tune == 2 || (tune == 0 && s <= 2.0f)) return lcv2::launch_pt<2, 16, 16, 8, 64, 32, 2, 3>(p, st);
+        if (tune == 1 || (tune == 7 && s <= 1.2f)) return lcv2::launch_pt<2, 16, 16, 8, 64, 24, 2, 3>(p, st);
+        if (tune == 2 || (tune == 7 && s <= 2.0f)) return lcv2::launch_pt<2, 16, 16, 8, 64, 32, 2, 3>(p, st);
         if (tune == 4) return lcv2::launch_pt<2, 16, 16, 8, 56, 32, 4, 2>(p, st);
         if (tune == 5) return lcv2::launch_pt<2, 16, 8, 16, 40, 48, 2, 3>(p, st);    // warp = 4 lattice rows x 8 points
         if (tune == 6) return lcv2::launch_pt<2, 16, 8, 16, 64, 48, 2, 3>(p, st);
