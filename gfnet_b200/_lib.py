@@ -16,7 +16,7 @@ EXPORTS = [
     "gfb_local_corr_tc2_run_f32",
     "gfb_global_match_f32", "gfb_pos_embed_f32", "gfb_kde_f32", "gfb_kde_sym_workspace_bytes", "gfb_kde_sym_f32", "gfb_match_postprocess_f32",
     "gfb_sample_keys_f32", "gfb_balance_keys_f32", "gfb_gather_matches_f32", "gfb_topk_workspace_bytes",
-    "gfb_topk_desc_f32", "gfb_homography_workspace_bytes", "gfb_homography_f32", "gfb_corner_error_f64",
+    "gfb_topk_desc_f32", "gfb_homography_workspace_bytes", "gfb_homography_f32", "gfb_homography_cv_f32", "gfb_corner_error_f64",
 ]
 
 GFB_EINVAL, GFB_EUNSUPPORTED, GFB_EALIGN, GFB_EWORKSPACE, GFB_ENODEVICE = -1, -2, -3, -4, -5
@@ -70,6 +70,7 @@ def _load():
     lib.gfb_homography_workspace_bytes.restype = sz
     lib.gfb_homography_workspace_bytes.argtypes = [i32, i32, i32]
     lib.gfb_homography_f32.argtypes = [vp, vp, i32, i32, f32, f32, f32, f32, i32, f32, i32, u32, vp, vp, vp, vp, vp, sz, vp]
+    lib.gfb_homography_cv_f32.argtypes = [vp, i32, i32, f32, f32, f32, f32, f32, i32, ctypes.c_double, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.gfb_corner_error_f64.argtypes = [vp, vp, vp, i32, f32, f32, f32, vp]
     for name in EXPORTS:   # getattr raises AttributeError if the library lacks a declared symbol
         if name not in ("gfb_strerror", "gfb_topk_workspace_bytes", "gfb_homography_workspace_bytes",

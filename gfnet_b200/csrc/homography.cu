@@ -38,7 +38,20 @@ struct HgParams {
     unsigned char* mask;
     unsigned long long* best;  // [B] packed (count << 32 | ~hyp)
     double* hyp_H;             // [B, n_hyp, 9]
+    int cv_mode;               // 1: OpenCV's own RANSAC loop (cv_ransac_kernel), float32 inlier test, mask from the final H
+    int max_iters;             // cv_mode: cv2 maxIters (2000)
+    double confidence;         // cv_mode: cv2 confidence
+    int* iters_out;            // cv_mode: RANSAC iterations OpenCV's loop ran (or null)
 };
+
+// OpenCV HomographyEstimatorCallback::computeError, float32 exactly as compiled there (no contraction)
+__device__ __forceinline__ float cv_err_f32(const float (&Hf)[8], float X, float Y, float x, float y) {
+    const float den = __fadd_rn(__fadd_rn(__fmul_rn(Hf[6], X), __fmul_rn(Hf[7], Y)), 1.f);
+    const float ww = __fdiv_rn(1.f, den);
+    const float dx = __fsub_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(Hf[0], X), __fmul_rn(Hf[1], Y)), Hf[2]), ww), x);
+    const float dy = __fsub_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(Hf[3], X), __fmul_rn(Hf[4], Y)), Hf[5]), ww), y);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
 
 // normalised -> pixel exactly as numpy float32 does it: (w-1) * (x + 1) / 2   (estimation.py:26-45)
 __device__ __forceinline__ void to_pixels(const HgParams& p, float4 m, float& ax, float& ay, float& bx, float& by) {
@@ -137,6 +150,167 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_kernel(HgParams p) {
     atomicMax(p.best + b, packed);
 }
 
+
+// =====================================================================================================================
+// cv_ransac_kernel: OpenCV's RANSACPointSetRegistrator::run for the homography callback, restated step by step
+// (modules/calib3d/src/ptsetreg.cpp, fundam.cpp, 4.x; the reference calls it through cv2.findHomography, estimation.py:66-72)
+// =====================================================================================================================
+//   RNG rng((uint64)-1): state = (uint32)state * 4164903690 + (state >> 32); uniform(0, n) = next() % n
+//   getSubset: 4 distinct indices, redrawn while a duplicate; the attempt is rejected (and 4 new indices drawn) when
+//              checkSubset fails: last point collinear with a pair of the others (in either image), or the
+//              orientation of the 4 point triples not preserved
+//   runKernel on the 4 points (exact 8x8 solve here: same model up to rounding), computeError in float32, inliers err <= thr^2
+//   best = most inliers so far (strictly more than before and > 3); niters = RANSACUpdateNumIters(confidence, outlier ratio)
+// The loop is sequential in OpenCV; here a CTA per pair runs it in rounds of CV_ATT attempts: thread 0 advances the RNG
+// (the draws do not depend on the data), the subset checks, minimal solves and inlier counts of a round run in parallel,
+// then thread 0 replays the round in order with OpenCV's update rule and stops where OpenCV stops.
+constexpr int CV_ATT = 64, CV_THREADS = 256;
+
+__device__ __forceinline__ bool cv_collinear_last(const float4 (&q)[4], bool second) {
+    // haveCollinearPoints(m, 4): is point 3 on a line through two of points 0..2 (or too close)
+    const float xi = second ? q[3].z : q[3].x, yi = second ? q[3].w : q[3].y;
+    for (int j = 0; j < 3; ++j) {
+        const double dx1 = (double)(second ? q[j].z : q[j].x) - xi, dy1 = (double)(second ? q[j].w : q[j].y) - yi;
+        for (int k = 0; k < j; ++k) {
+            const double dx2 = (double)(second ? q[k].z : q[k].x) - xi, dy2 = (double)(second ? q[k].w : q[k].y) - yi;
+            if (fabs(dx2 * dy1 - dy2 * dx1) <= 1.1920928955078125e-07 * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2))) return true;
+        }
+    }
+    return false;
+}
+__device__ __forceinline__ double cv_det3(double a0, double a1, double b0, double b1, double c0, double c1) {
+    // determinant of [[a0,a1,1],[b0,b1,1],[c0,c1,1]] (cv::determinant of a Matx33d)
+    return a0 * (b1 - c1) - a1 * (b0 - c0) + (b0 * c1 - b1 * c0);
+}
+__device__ bool cv_check_subset(const float4 (&q)[4]) {
+    if (cv_collinear_last(q, false) || cv_collinear_last(q, true)) return false;
+    const int tt[4][3] = {{0, 1, 2}, {1, 2, 3}, {0, 2, 3}, {0, 1, 3}};
+    int negative = 0;
+    for (int i = 0; i < 4; ++i) {
+        const int* t = tt[i];
+        const double dA = cv_det3(q[t[0]].x, q[t[0]].y, q[t[1]].x, q[t[1]].y, q[t[2]].x, q[t[2]].y);
+        const double dB = cv_det3(q[t[0]].z, q[t[0]].w, q[t[1]].z, q[t[1]].w, q[t[2]].z, q[t[2]].w);
+        negative += dA * dB < 0;
+    }
+    return negative == 0 || negative == 4;
+}
+__device__ int cv_update_num_iters(double p, double ep, int max_iters) {   // RANSACUpdateNumIters, modelPoints = 4
+    p = fmin(fmax(p, 0.), 1.); ep = fmin(fmax(ep, 0.), 1.);
+    double num = fmax(1. - p, 2.2250738585072014e-308);
+    double denom = 1. - pow(1. - ep, 4.0);
+    if (denom < 2.2250738585072014e-308) return 0;
+    num = log(num); denom = log(denom);
+    return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
+}
+
+__global__ void __launch_bounds__(CV_THREADS) cv_ransac_kernel(HgParams p) {
+    extern __shared__ float4 spts[];                 // pixel coords (ax, ay, bx, by) of all N points of this pair
+    __shared__ int s_idx[CV_ATT][4];
+    __shared__ int s_valid[CV_ATT], s_good[CV_ATT];
+    __shared__ float s_Hf[CV_ATT][8];
+    __shared__ double s_H[CV_ATT][9];
+    __shared__ unsigned long long s_rng;
+    __shared__ int s_iter, s_niters, s_maxgood, s_done, s_best_set;
+    __shared__ double s_bestH[9];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float4* mb = reinterpret_cast<const float4*>(p.matches) + (size_t)b * p.N;
+    for (int i = tid; i < p.N; i += CV_THREADS) {
+        float4 m = __ldg(mb + i), q;
+        to_pixels(p, m, q.x, q.y, q.z, q.w);
+        spts[i] = q;
+    }
+    if (tid == 0) { s_rng = 0xFFFFFFFFFFFFFFFFull; s_iter = 0; s_niters = p.max_iters; s_maxgood = 0; s_done = 0; s_best_set = 0; }
+    __syncthreads();
+    const float thr = p.thr2;
+    for (int round = 0; round < 100000; ++round) {
+        if (tid == 0) {                                // the RNG stream: 4 distinct indices per attempt
+            unsigned long long st = s_rng;
+            const unsigned n = (unsigned)p.N;
+            for (int a = 0; a < CV_ATT; ++a) {
+                int id[4];
+                for (int i = 0; i < 4; ++i) {
+                    bool dup;
+                    int v;
+                    do {
+                        st = (unsigned long long)(unsigned)st * 4164903690ull + (st >> 32);
+                        v = (int)((unsigned)st % n);
+                        dup = false;
+                        for (int e = 0; e < i; ++e) dup |= id[e] == v;
+                    } while (dup);
+                    id[i] = v;
+                }
+                for (int i = 0; i < 4; ++i) s_idx[a][i] = id[i];
+            }
+            s_rng = st;
+        }
+        __syncthreads();
+        if (tid < CV_ATT) {                            // subset check + minimal model, one attempt per thread
+            float4 q[4];
+            for (int e = 0; e < 4; ++e) q[e] = spts[s_idx[tid][e]];
+            int valid = cv_check_subset(q) ? 1 : 0;    // 0: rejected inside getSubset (not an iteration)
+            if (valid) {
+                double M[8][9];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double X = q[e].x, Y = q[e].y, x = q[e].z, y = q[e].w;
+                    M[2 * e][0] = X; M[2 * e][1] = Y; M[2 * e][2] = 1; M[2 * e][3] = 0; M[2 * e][4] = 0; M[2 * e][5] = 0;
+                    M[2 * e][6] = -x * X; M[2 * e][7] = -x * Y; M[2 * e][8] = x;
+                    M[2 * e + 1][0] = 0; M[2 * e + 1][1] = 0; M[2 * e + 1][2] = 0; M[2 * e + 1][3] = X; M[2 * e + 1][4] = Y; M[2 * e + 1][5] = 1;
+                    M[2 * e + 1][6] = -y * X; M[2 * e + 1][7] = -y * Y; M[2 * e + 1][8] = y;
+                }
+                bool ok = solve8(M);
+                for (int e = 0; e < 8; ++e) ok = ok && isfinite(M[e][8]);
+                if (ok) {
+                    for (int e = 0; e < 8; ++e) { s_H[tid][e] = M[e][8]; s_Hf[tid][e] = (float)M[e][8]; }
+                    s_H[tid][8] = 1.0;
+                } else {
+                    valid = 2;                         // an iteration without a model (runKernel returned 0 models)
+                }
+            }
+            s_valid[tid] = valid;
+            s_good[tid] = 0;
+        }
+        __syncthreads();
+        for (int a = warp; a < CV_ATT; a += CV_THREADS / 32) {      // inlier counts, one attempt per warp at a time
+            if (s_valid[a] != 1) continue;
+            float Hf[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) Hf[e] = s_Hf[a][e];
+            int cnt = 0;
+            for (int i = lane; i < p.N; i += 32) {
+                const float4 q = spts[i];
+                cnt += cv_err_f32(Hf, q.x, q.y, q.z, q.w) <= thr;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (lane == 0) s_good[a] = cnt;
+        }
+        __syncthreads();
+        if (tid == 0) {                                // OpenCV's loop over the round, in order
+            int iter = s_iter, niters = s_niters, maxgood = s_maxgood;
+            for (int a = 0; a < CV_ATT && iter < niters; ++a) {
+                if (s_valid[a] == 0) continue;
+                if (s_valid[a] == 1 && s_good[a] > max(maxgood, 3)) {
+                    maxgood = s_good[a];
+                    for (int e = 0; e < 9; ++e) s_bestH[e] = s_H[a][e];
+                    s_best_set = 1;
+                    niters = cv_update_num_iters(p.confidence, (double)(p.N - maxgood) / p.N, niters);
+                }
+                ++iter;
+            }
+            s_iter = iter; s_niters = niters; s_maxgood = maxgood;
+            s_done = iter >= niters;
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    if (tid < 9) p.hyp_H[(size_t)b * 9 + tid] = s_best_set ? s_bestH[tid] : 0.0;
+    if (tid == 0) {
+        p.best[b] = ((unsigned long long)(unsigned)(s_best_set ? s_maxgood : 0) << 32) | 0xFFFFFFFFull;     // hypothesis 0
+        if (p.iters_out) p.iters_out[b] = s_iter;
+    }
+}
+
 // ---- block reduction of NACC doubles: result in sm_out[0..NACC) ---------------------------------
 constexpr int RF_THREADS = 512;
 template <int NACC>
@@ -194,6 +368,41 @@ __device__ void jacobi9_smallest(double* A /*81*/, double* V /*81*/, double* out
     for (int k = 0; k < 9; ++k) out[k] = V[k * 9 + best];
 }
 
+// Smallest eigenvector of a symmetric positive semi-definite 9x9 by shifted inverse iteration (Cholesky of A + mu I, six
+// solves): LtL of a homography fit has one eigenvalue far below the rest, so the iteration converges in 2-3 steps; a
+// single thread needs ~1.5k flops instead of the ~60k of a cyclic Jacobi sweep series.  false -> caller falls back to Jacobi.
+__device__ bool inv_iter9_smallest(const double* A /*81*/, double* L /*81*/, double* out /*9*/) {
+    double tr = 0;
+    for (int i = 0; i < 9; ++i) tr += A[i * 9 + i];
+    if (!(tr > 0.0) || !isfinite(tr)) return false;
+    const double mu = tr * 1e-15;
+    for (int j = 0; j < 9; ++j) {
+        double d = A[j * 9 + j] + mu;
+        for (int k = 0; k < j; ++k) d -= L[j * 9 + k] * L[j * 9 + k];
+        if (!(d > tr * 1e-18)) return false;
+        d = sqrt(d);
+        L[j * 9 + j] = d;
+        for (int i = j + 1; i < 9; ++i) {
+            double v = A[i * 9 + j];
+            for (int k = 0; k < j; ++k) v -= L[i * 9 + k] * L[j * 9 + k];
+            L[i * 9 + j] = v / d;
+        }
+    }
+    double x[9], y[9];
+    for (int i = 0; i < 9; ++i) x[i] = 1.0 / 3.0 + 0.01 * i;
+    for (int it = 0; it < 6; ++it) {
+        for (int i = 0; i < 9; ++i) { double v = x[i]; for (int k = 0; k < i; ++k) v -= L[i * 9 + k] * y[k]; y[i] = v / L[i * 9 + i]; }
+        for (int i = 8; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 9; ++k) v -= L[k * 9 + i] * x[k]; x[i] = v / L[i * 9 + i]; }
+        double nrm = 0;
+        for (int i = 0; i < 9; ++i) nrm += x[i] * x[i];
+        nrm = sqrt(nrm);
+        if (!(nrm > 0.0) || !isfinite(nrm)) return false;
+        for (int i = 0; i < 9; ++i) x[i] /= nrm;
+    }
+    for (int i = 0; i < 9; ++i) out[i] = x[i];
+    return true;
+}
+
 __global__ void __launch_bounds__(RF_THREADS) refit_kernel(HgParams p) {
     extern __shared__ float s_w[];           // [N] weight of every point (0 = not an inlier), filled by the first pass
     __shared__ double sm_part[(RF_THREADS / 32) * 30];
@@ -222,9 +431,13 @@ __global__ void __launch_bounds__(RF_THREADS) refit_kernel(HgParams p) {
         const double* hs = p.hyp_H + ((size_t)b * p.n_hyp + hyp) * 9;
         for (int e = 0; e < 9; ++e) hb[e] = hs[e];
     }
+    float hbf[8];
+    for (int e = 0; e < 8; ++e) hbf[e] = use_model ? (float)hb[e] : 0.f;
     auto weight_of = [&](int i, const float4& q) -> double {
         double w = wb ? (double)wb[i] : 1.0;
-        if (use_model) {
+        if (use_model && p.cv_mode) {
+            if (!(cv_err_f32(hbf, q.x, q.y, q.z, q.w) <= p.thr2)) w = 0.0;
+        } else if (use_model) {
             const double X = q.x, Y = q.y;
             const double ww = 1.0 / (hb[6] * X + hb[7] * Y + 1.0);
             const double dx = (hb[0] * X + hb[1] * Y + hb[2]) * ww - (double)q.z;
@@ -285,7 +498,7 @@ __global__ void __launch_bounds__(RF_THREADS) refit_kernel(HgParams p) {
                 sA[(3 + i) * 9 + j] = 0.0;     sA[(3 + i) * 9 + 3 + j] = s0;      sA[(3 + i) * 9 + 6 + j] = -sy;
                 sA[(6 + i) * 9 + j] = -sx;     sA[(6 + i) * 9 + 3 + j] = -sy;     sA[(6 + i) * 9 + 6 + j] = sq;
             }
-        jacobi9_smallest(sA, sV, sh);
+        if (!inv_iter9_smallest(sA, sV, sh)) jacobi9_smallest(sA, sV, sh);
         // H = invNormB * H0 * NormA, then / h33
         const double iB[9] = {1.0 / sBx, 0, cBx, 0, 1.0 / sBy, cBy, 0, 0, 1};
         const double nA[9] = {sAx, 0, -cAx * sAx, 0, sAy, -cAy * sAy, 0, 0, 1};
@@ -370,6 +583,22 @@ __global__ void __launch_bounds__(RF_THREADS) refit_kernel(HgParams p) {
         __syncthreads();
     }
     if (threadIdx.x < 9) p.H_out[(size_t)b * 9 + threadIdx.x] = threadIdx.x == 8 ? 1.0 : sH[threadIdx.x];
+    if (p.cv_mode) {
+        // cv2.findHomography returns the mask of the REFINED model (float32 computeError <= thr^2), checked against 4.13
+        float hf[8];
+        for (int e = 0; e < 8; ++e) hf[e] = (float)sH[e];
+        double c1[1] = {0};
+        for (int i = threadIdx.x; i < p.N; i += RF_THREADS) {
+            float4 q; to_pixels(p, __ldg(mb + i), q.x, q.y, q.z, q.w);
+            const bool in = cv_err_f32(hf, q.x, q.y, q.z, q.w) <= p.thr2;
+            if (mk) mk[i] = in;
+            c1[0] += in;
+        }
+        __syncthreads();
+        block_reduce<1>(c1, sm_part, sm_red);
+        if (threadIdx.x == 0) { p.status[b] = 1; p.n_inl[b] = (int)(sm_red[0] + 0.5); }
+        return;
+    }
     if (threadIdx.x == 0) { p.status[b] = 1; p.n_inl[b] = s_cnt; }
 }
 
@@ -424,6 +653,7 @@ extern "C" int gfb_homography_f32(const float* matches, const float* weights, in
     p.pixel_in = (wq == 0.f);
     p.wq1 = wq - 1.f; p.hq1 = hq - 1.f; p.ws1 = wsup - 1.f; p.hs1 = hsup - 1.f;
     p.n_hyp = n_hyp; p.thr2 = thresh * thresh; p.gn_iters = gn_iters; p.seed = seed;
+    p.cv_mode = 0; p.max_iters = 0; p.confidence = 0.0; p.iters_out = nullptr;
     p.H_out = H_out; p.status = status; p.n_inl = n_inliers; p.mask = mask_out;
     p.best = reinterpret_cast<unsigned long long*>(workspace);
     p.hyp_H = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + (((size_t)B * 8 + 15) / 16) * 16);
@@ -441,6 +671,40 @@ extern "C" int gfb_homography_f32(const float* matches, const float* weights, in
     if (rsmem > 200 * 1024) return GFB_EUNSUPPORTED;
     cudaError_t e2 = cudaFuncSetAttribute(refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
     if (e2 != cudaSuccess) return (int)e2;
+    refit_kernel<<<B, RF_THREADS, rsmem, st>>>(p);
+    GFB_LAUNCH_RESULT();
+}
+
+// cv2.findHomography(pos_a, pos_b, cv2.RANSAC, thresh, maxIters, confidence) restated on the device (estimation.py:66-72):
+// OpenCV's RNG, subset checks, adaptive iteration count, refit on the inliers, refinement, mask of the refined model.
+extern "C" int gfb_homography_cv_f32(const float* matches, int B, int N, float wq, float hq, float wsup, float hsup,
+                                     float thresh, int max_iters, double confidence, int gn_iters,
+                                     double* H_out, int* status, int* n_inliers, unsigned char* mask_out, int* iters_out,
+                                     void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
+    GFB_CHECK_ARG(matches && H_out && status && n_inliers && B > 0 && N >= 5 && max_iters > 0 && gn_iters >= 0 && gn_iters <= 100);
+    GFB_CHECK_ARG(B <= 65535 && thresh > 0.f && confidence > 0.0 && confidence < 1.0);
+    if (!gfb_aligned(matches, 16)) return GFB_EALIGN;
+    if (!workspace || workspace_bytes < gfb_homography_workspace_bytes(B, N, 1) || !gfb_aligned(workspace, 8)) return GFB_EWORKSPACE;
+    const size_t smem = (size_t)N * sizeof(float4);
+    if (smem > 180 * 1024) return GFB_EUNSUPPORTED;
+    HgParams p;
+    p.matches = matches; p.weights = nullptr; p.B = B; p.N = N;
+    p.pixel_in = (wq == 0.f);
+    p.wq1 = wq - 1.f; p.hq1 = hq - 1.f; p.ws1 = wsup - 1.f; p.hs1 = hsup - 1.f;
+    p.n_hyp = 1; p.thr2 = thresh * thresh; p.gn_iters = gn_iters; p.seed = 0;
+    p.H_out = H_out; p.status = status; p.n_inl = n_inliers; p.mask = mask_out;
+    p.best = reinterpret_cast<unsigned long long*>(workspace);
+    p.hyp_H = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + (((size_t)B * 8 + 15) / 16) * 16);
+    p.cv_mode = 1; p.max_iters = max_iters; p.confidence = confidence; p.iters_out = iters_out;
+    cudaStream_t st = gfb_cu(stream);
+    cudaError_t e = cudaFuncSetAttribute(cv_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cv_ransac_kernel<<<B, CV_THREADS, smem, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const size_t rsmem = (size_t)N * sizeof(float);
+    e = cudaFuncSetAttribute(refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+    if (e != cudaSuccess) return (int)e;
     refit_kernel<<<B, RF_THREADS, rsmem, st>>>(p);
     GFB_LAUNCH_RESULT();
 }

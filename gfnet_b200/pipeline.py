@@ -12,7 +12,8 @@ from . import ops, matcher, estimation
 
 
 class HotPath:
-    def __init__(self, num_samples=5000, n_hyp=512, precision=0, lc_algo=0, seed=0):
+    def __init__(self, num_samples=5000, n_hyp=None, precision=0, lc_algo=0, seed=0):
+        # n_hyp None = OpenCV's own RANSAC loop on the device (cv2.findHomography parity), K > 0 = fixed hash-drawn budget
         self.num_samples, self.n_hyp, self.precision, self.lc_algo, self.seed = num_samples, n_hyp, precision, lc_algo, seed
         self._corr = {}
         self.timing = None    # list of (key, start_event, end_event) when bench.py wants per-launch device times
@@ -32,7 +33,7 @@ class HotPath:
                 b = sc["f1"].shape[0]
                 n += ops.local_correlation_launches(b, sc["c"], sc["hs"], sc["hs"], sc["G"], sc["r"], calls=len(sc["flows"]))
         n += 1 + 1 + 1 + 1 + 5 + 1 + 1 + 1                      # postprocess, keys, topk, gather, kde (keys, sort, gather+boxes, symmetric, finish), balance, topk, gather
-        n += (2 if self.n_hyp > 0 else 0) + 1 + 1               # init+ransac, refit, corner error
+        n += (1 if self.n_hyp is None else 2 if self.n_hyp > 0 else 0) + 1 + 1   # (cv ransac | init + ransac), refit, corner error
         return n
 
     def run(self, batch, generator=None, noise=None):

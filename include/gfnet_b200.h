@@ -203,6 +203,17 @@ int gfb_homography_f32(const float* matches, const float* weights, int B, int N,
                        int n_hyp, float thresh, int gn_iters, unsigned seed,
                        double* H_out, int* status, int* n_inliers, unsigned char* mask_out,
                        void* workspace, size_t workspace_bytes, gfb_stream_t stream);
+/* cv2.findHomography(pos_a, pos_b, cv2.RANSAC, ransacReprojThreshold, maxIters, confidence) restated on the device, batched
+ * over pairs -- replaces the host call at estimation.py:66-72 (OpenCV itself is an un-vendored, un-pinned dependency of the
+ * reference, requirements.txt:2; the restatement follows modules/calib3d/src/ptsetreg.cpp + fundam.cpp of 4.x and is pinned
+ * on cv2 4.13.0 fixtures): RNG((uint64)-1) subset draws, checkSubset (collinearity + orientation), 4-point models scored by
+ * the float32 transfer error, adaptive iteration count (RANSACUpdateNumIters), refit on the winner's inliers (normalised
+ * DLT) + refinement, and the returned mask = inliers of the REFINED model.  iters_out [B] (or NULL) = iterations OpenCV's
+ * loop runs.  matches [B,N,4] normalised (wq == 0: already pixels).  workspace >= gfb_homography_workspace_bytes(B, N, 1). */
+int gfb_homography_cv_f32(const float* matches, int B, int N, float wq, float hq, float wsup, float hsup,
+                          float thresh, int max_iters, double confidence, int gn_iters,
+                          double* H_out, int* status, int* n_inliers, unsigned char* mask_out, int* iters_out,
+                          void* workspace, size_t workspace_bytes, gfb_stream_t stream);
 /* err[b] = min(clip, mean_k || proj(H_gt[b] c_k) - proj(H_pred[b] c_k) ||), c_k the 4 corners. */
 int gfb_corner_error_f64(const double* H_pred, const double* H_gt, float* err, int B,
                          float w, float h, float clip, gfb_stream_t stream);

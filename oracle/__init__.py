@@ -27,6 +27,6 @@ from .sampling import (match_postprocess_port, multinomial_from_noise, sample_po
                        balanced_probability)
 from .estimation import (convert_coordinates, corner_error, auc, fallback_homography,
                          find_homography_cv2, weighted_dlt, refine_homography_lm,
-                         homography_from_matches)
+                         homography_from_matches, find_homography_cv_restated, cv_compute_error_f32)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -256,6 +256,125 @@ def homography_ransac_def(pa, pb, seed=0, pair=0, nhyp=512, thresh=3.0, gn_iters
     return H, best_mask.astype(np.uint8), True
 
 
+# --- OpenCV's RANSAC for cv2.findHomography, restated step by step -------------------------------------------------
+# Source restated: OpenCV 4.x modules/calib3d/src/ptsetreg.cpp (RANSACPointSetRegistrator::run / getSubset,
+# RANSACUpdateNumIters) and fundam.cpp (HomographyEstimatorCallback::checkSubset / runKernel / computeError,
+# findHomography's refit + LM refinement + mask).  Pinned on cv2 4.13.0: tests/golden/homography_cv2_grid.npz
+# (generated by tests/golden/make_homography_grid.py with the reference's exact call, estimation.py:66-72).
+CV_RNG_COEFF = 4164903690
+_FLT_EPS = float(np.finfo(np.float32).eps)
+_DBL_MIN = float(np.finfo(np.float64).tiny)
+
+
+class CvRNG:
+    """cv::RNG (multiply-with-carry); findHomography seeds it with (uint64)-1."""
+
+    def __init__(self, state=0xFFFFFFFFFFFFFFFF):
+        self.state = state
+
+    def next(self):
+        self.state = ((self.state & 0xFFFFFFFF) * CV_RNG_COEFF + (self.state >> 32)) & 0xFFFFFFFFFFFFFFFF
+        return self.state & 0xFFFFFFFF
+
+    def uniform(self, a, b):
+        return a if a == b else int(self.next() % (b - a) + a)
+
+
+def _cv_collinear_last(pts):
+    i = len(pts) - 1
+    for j in range(i):
+        dx1, dy1 = float(pts[j][0]) - float(pts[i][0]), float(pts[j][1]) - float(pts[i][1])
+        for k in range(j):
+            dx2, dy2 = float(pts[k][0]) - float(pts[i][0]), float(pts[k][1]) - float(pts[i][1])
+            if abs(dx2 * dy1 - dy2 * dx1) <= _FLT_EPS * (abs(dx1) + abs(dy1) + abs(dx2) + abs(dy2)):
+                return True
+    return False
+
+
+def cv_check_subset(ms1, ms2):
+    """HomographyEstimatorCallback::checkSubset for 4 correspondences."""
+    if _cv_collinear_last(ms1) or _cv_collinear_last(ms2):
+        return False
+    negative = 0
+    for t in ((0, 1, 2), (1, 2, 3), (0, 2, 3), (0, 1, 3)):
+        A = np.array([[ms1[i][0], ms1[i][1], 1.0] for i in t], dtype=np.float64)
+        B = np.array([[ms2[i][0], ms2[i][1], 1.0] for i in t], dtype=np.float64)
+        negative += bool(np.linalg.det(A) * np.linalg.det(B) < 0)
+    return negative in (0, 4)
+
+
+def cv_update_num_iters(p, ep, model_points, max_iters):
+    """RANSACUpdateNumIters."""
+    p = min(max(p, 0.0), 1.0)
+    ep = min(max(ep, 0.0), 1.0)
+    num = max(1.0 - p, _DBL_MIN)
+    denom = 1.0 - (1.0 - ep) ** model_points
+    if denom < _DBL_MIN:
+        return 0
+    num, denom = np.log(num), np.log(denom)
+    return max_iters if (denom >= 0 or -num >= max_iters * (-denom)) else int(np.rint(num / denom))
+
+
+def cv_compute_error_f32(H, m1, m2):
+    """HomographyEstimatorCallback::computeError: float32 arithmetic on the float-cast model."""
+    Hf = np.asarray(H, dtype=np.float64).reshape(9).astype(np.float32)
+    M, m = np.asarray(m1, dtype=np.float32), np.asarray(m2, dtype=np.float32)
+    one = np.float32(1)
+    ww = one / (Hf[6] * M[:, 0] + Hf[7] * M[:, 1] + one)
+    dx = (Hf[0] * M[:, 0] + Hf[1] * M[:, 1] + Hf[2]) * ww - m[:, 0]
+    dy = (Hf[3] * M[:, 0] + Hf[4] * M[:, 1] + Hf[5]) * ww - m[:, 1]
+    return dx * dx + dy * dy
+
+
+def find_homography_cv_restated(pos_a, pos_b, thresh=3.0, confidence=0.99999, max_iters=2000, refine_iters=10):
+    """cv2.findHomography(pos_a, pos_b, cv2.RANSAC, thresh, maxIters=2000, confidence) without cv2.
+
+    Returns (H 3x3 float64, mask uint8 [N] of the refined model, ok, ransac iterations).
+    """
+    pa, pb = np.asarray(pos_a, dtype=np.float32), np.asarray(pos_b, dtype=np.float32)
+    count = len(pa)
+    if count < 5:
+        raise ValueError("restated for count > 4 (the reference samples 5 000 matches)")
+    rng = CvRNG()
+    niters, it, max_good = max_iters, 0, 0
+    t = np.float32(thresh * thresh)
+    best_mask = None
+    while it < niters:
+        idx, attempts = None, 0
+        while attempts < 10000:                      # getSubset
+            cand = []
+            for _ in range(4):
+                v = rng.uniform(0, count)
+                while v in cand:
+                    v = rng.uniform(0, count)
+                cand.append(v)
+            if cv_check_subset(pa[cand], pb[cand]):
+                idx = cand
+                break
+            attempts += 1
+        if idx is None:
+            if it == 0:
+                return fallback_homography(), np.zeros(count, np.uint8), False, it
+            break
+        H4, ok = weighted_dlt(pa[idx].astype(np.float64), pb[idx].astype(np.float64))       # runKernel on the sample
+        if ok:
+            mask = cv_compute_error_f32(H4, pa, pb) <= t
+            good = int(mask.sum())
+            if good > max(max_good, 3):
+                best_mask, max_good = mask, good
+                niters = cv_update_num_iters(confidence, (count - good) / count, 4, niters)
+        it += 1
+    if best_mask is None:
+        return fallback_homography(), np.zeros(count, np.uint8), False, it
+    w = best_mask.astype(np.float64)
+    H, ok = weighted_dlt(pa.astype(np.float64), pb.astype(np.float64), w)                   # runKernel on the inliers
+    if not ok:
+        return fallback_homography(), np.zeros(count, np.uint8), False, it
+    H = refine_homography_lm(H, pa.astype(np.float64), pb.astype(np.float64), w, iters=refine_iters)   # LMSolver(10)
+    final_mask = (cv_compute_error_f32(H, pa, pb) <= t).astype(np.uint8)                    # mask of the refined model
+    return H, final_mask, True, it
+
+
 def homography_from_matches(matches, wq, hq, wsup, hsup, H_gt=None, solver="cv2", **kw):
     """matches[N,4] (normalised) -> pixel coords -> H -> corner error; reference: estimation.py:60-92."""
     m = np.asarray(matches, dtype=np.float32)

@@ -1,6 +1,12 @@
-"""CPU hot path for one batch of pairs, built from the oracle ports in the reference's call order
-(SURVEY.md 3.1).  TEST INFRASTRUCTURE / CPU BASELINE ONLY (bench.py ``cpu_baseline`` and
-``--impl reference``): this is what the reference's own functions cost on host cores."""
+"""CPU hot path for one batch of pairs, in the reference's call order.
+TEST INFRASTRUCTURE / CPU BASELINE ONLY (tests, bench.py ``cpu_baseline`` and ``--impl reference``).
+
+``impl="reference"`` calls the REFERENCE'S OWN functions (oracle.reference: ``local_correlation``,
+``GFNet.corr_volume`` / ``pos_embed`` / ``sample`` -> ``kde``) plus ``cv2.findHomography`` exactly as estimation.py:66-72
+does; the two stretches of the reference that cannot be imported (the tail of ``GFNet.match``, model/network.py:358-384,
+which is inline in a method that needs the backbone, and estimation.py, which imports kornia) are the oracle ports.
+``impl="port"`` uses the oracle ports throughout (same torch / cv2 operators in the same order).
+"""
 import time
 
 import numpy as np
@@ -12,41 +18,62 @@ from .sampling import match_postprocess_port, sample_port
 from .estimation import convert_coordinates, find_homography_cv2, corner_error
 
 
-def cpu_hot_path(batch, num_samples=5000, seed=0, timings=None):
-    """``batch``: a gfnet_b200.synth.PairBatch living on the CPU.  Returns (H list, err list)."""
+def cpu_hot_path(batch, num_samples=5000, seed=0, timings=None, impl="port", noise=None, kde_down=8, return_matches=False):
+    """``batch``: a gfnet_b200.synth.PairBatch living on the CPU.  Returns (H list, err list[, matches list]).
+
+    ``noise = (q1 [B,n], q2 [B,n1])``: the two Exp(1) draws of ``torch.multinomial`` (port only; the reference's
+    ``GFNet.sample`` draws them itself from the global generator, seeded with ``seed``).
+    """
     t = {} if timings is None else timings
+    ref = None
+    if impl == "reference":
+        from . import reference as R
+        ref = R.load_reference()
+        self_ = R.SampleSelf()
+        torch.manual_seed(seed)
 
     def tick(name, t0):
         t[name] = t.get(name, 0.0) + time.perf_counter() - t0
 
     t0 = time.perf_counter()
-    flow = pos_embed_port(corr_volume_port(batch.coarse_f0, batch.coarse_f1))       # network.py:251-252
+    if ref is not None:
+        flow = ref.GFNet.pos_embed(self_, ref.GFNet.corr_volume(self_, batch.coarse_f0, batch.coarse_f1))   # network.py:251-252
+    else:
+        flow = pos_embed_port(corr_volume_port(batch.coarse_f0, batch.coarse_f1))
     tick("coarse_match", t0)
     t0 = time.perf_counter()
+    lc = ref.local_correlation if ref is not None else local_correlation_port
     for scales in batch.passes:
         for sc in scales:
             b, c, hs, G, r = sc["f1"].shape[0], sc["c"], sc["hs"], sc["G"], sc["r"]
             for fl in sc["flows"]:
-                local_correlation_port((b, c, hs, hs), sc["f0"], sc["f1"], r, G, flow=fl)   # network.py:553
+                lc((b, c, hs, hs), sc["f0"], sc["f1"], r, G, flow=fl)                                        # network.py:553
     tick("local_correlation", t0)
     t0 = time.perf_counter()
-    warp, cert = match_postprocess_port(batch.final_flow, batch.cert_logits, symmetric=True)  # :358-384
+    warp, cert = match_postprocess_port(batch.final_flow, batch.cert_logits, symmetric=True)                 # :358-384
     tick("match_postprocess", t0)
-    Hs, errs = [], []
+    Hs, errs, ms = [], [], []
     gen = torch.Generator().manual_seed(seed)
     res = batch.res
     for i in range(batch.B):
         t0 = time.perf_counter()
         n = cert[i].numel()
-        q1 = torch.empty(n).exponential_(1, generator=gen)
-        q2 = torch.empty(min(4 * num_samples, n)).exponential_(1, generator=gen)
-        m, c, _, _, _ = sample_port(warp[i], cert[i], num_samples, q1, q2, half=False, down=8)  # :385-414 (CPU: down=8)
+        if ref is not None:
+            m, c = ref.GFNet.sample(self_, warp[i], cert[i], num_samples)                                    # :385-414 (CPU: down=8)
+        else:
+            if noise is not None:
+                q1, q2 = noise[0][i], noise[1][i]
+            else:
+                q1 = torch.empty(n).exponential_(1, generator=gen)
+                q2 = torch.empty(min(4 * num_samples, n)).exponential_(1, generator=gen)
+            m, c, _, _, _ = sample_port(warp[i], cert[i], num_samples, q1, q2, half=False, down=kde_down)
         tick("sample_kde", t0)
         t0 = time.perf_counter()
         mn = m.numpy()
-        pa, pb = convert_coordinates(mn[:, :2], mn[:, 2:], res, res, res, res)          # estimation.py:62-64
-        H, _, _ = find_homography_cv2(pa, pb)                                            # :66-77
-        errs.append(corner_error(H, batch.H_gt[i].numpy(), res, res))                   # :79-92
+        pa, pb = convert_coordinates(mn[:, :2], mn[:, 2:], res, res, res, res)                               # estimation.py:62-64
+        H, _, _ = find_homography_cv2(pa, pb)                                                                # :66-77
+        errs.append(corner_error(H, batch.H_gt[i].numpy(), res, res))                                        # :79-92
         Hs.append(H)
+        ms.append(mn)
         tick("homography", t0)
-    return Hs, errs
+    return (Hs, errs, ms) if return_matches else (Hs, errs)

@@ -1,10 +1,14 @@
 """Pin the oracle against fixtures produced by the reference's own functions
 (tests/golden/make_golden.py) and against cv2.findHomography.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 import oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _lc_case(g, i):
@@ -138,3 +142,21 @@ def test_corner_error_and_auc():
 def test_convert_coordinates():
     a, b = oracle.convert_coordinates(np.array([[-1.0, 1.0]]), np.array([[0.0, 0.0]]), 448, 224, 560, 560)
     assert np.allclose(a, [[0, 223]]) and np.allclose(b, [[279.5, 279.5]])
+
+
+def test_opencv_ransac_restatement_against_cv2_grid(golden):
+    """oracle.find_homography_cv_restated (OpenCV's RNG, subset checks, adaptive iterations, refit, refinement, mask of the
+    refined model) against cv2 4.13.0 called as estimation.py:66-72 on the SURVEY 8(d2) grid at N = 5 000."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_homography_grid", os.path.join(GOLDEN, "make_homography_grid.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = golden("homography_cv2_grid")
+    assert int(g["ncases"]) == len(mg.CASES)
+    for i in range(len(mg.CASES) - 1):          # the 75 %-outlier case runs all 2 000 iterations: GPU test only (slow in numpy)
+        pa, pb, _ = mg.grid_case(i)
+        H, mask, ok, iters = oracle.find_homography_cv_restated(pa, pb)
+        ref_mask = np.unpackbits(g[f"c{i}_mask"])[:len(pa)]
+        err = oracle.corner_error(H, g[f"c{i}_H"], 448, 448)
+        assert ok and err < 1e-5, (i, err)
+        assert (mask != ref_mask).sum() == 0, (i, int((mask != ref_mask).sum()))
