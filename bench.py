@@ -3,13 +3,15 @@
 iteration / pass + post-process + balanced sampling with kde + homography + corner error).
 
   python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun)
-  python bench.py --impl reference --steps K --warmup W    the reference's CPU path (oracle port), rank 0 only
+  python bench.py --impl reference --steps K --warmup W    the reference's own CPU functions on host cores, rank 0 only
+  python bench.py --config map224|map672 ...               the other BASELINE.json workloads (native pyramids)
 
-Workload (BASELINE.json configs[1]): vis_ir.json, 448x448 pairs (+ the 560 upsample pass the reference
-always runs), num_itr = 2, 32 pairs per GPU (op batch 64, symmetric), synthetic pyramids / random H.
-One JSON line on stdout (rank 0).
+Default workload (BASELINE.json configs[1], the one the metric is quoted on): vis_ir.json, 448x448 pairs (+ the 560
+upsample pass the reference always runs), num_itr = 2, 32 pairs per GPU (op batch 64, symmetric), synthetic pyramids /
+random H.  One JSON line on stdout (rank 0).
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -22,8 +24,17 @@ sys.path.insert(0, ROOT)
 
 METRIC = "image pairs/s at 448^2 (corr+kde+H)"
 UNIT = "pairs/s"
-PAIRS_PER_GPU = 32
 NUM_ITR = 2
+# config -> (pairs per GPU, scaling): map672 is BASELINE config 4's fixed global batch of 64 (strong scaling)
+CONFIGS = {"visir448": (32, "weak"), "map224": (32, "weak"), "map672": (64, "strong")}
+
+
+def load_synth():
+    """gfnet_b200/synth.py without importing the package (the reference arm must not load our .so)."""
+    spec = importlib.util.spec_from_file_location("gfb_synth_standalone", os.path.join(ROOT, "gfnet_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def measured_peaks():
@@ -76,44 +87,72 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def config_dict(n_gpus, extra=None):
-    cfg = {"workload": "vis_ir.json 448x448 pairs (pass 1 at 448 + upsample pass at 560), num_itr=2, symmetric",
-           "pairs_per_gpu": PAIRS_PER_GPU, "global_pairs": PAIRS_PER_GPU * n_gpus, "num_samples": 5000,
-           "kde_points": 20000, "ransac_hypotheses": 512, "parallelism": f"pairs sharded over {n_gpus} GPU(s), one all_gather of [B,12]",
-           "l2": "inputs 1.3 GB + outputs 0.66 GB per step >> 126 MB L2 (no flush needed)"}
+def metric_name(args, synth):
+    return METRIC.replace("448", str(synth.WORKLOADS[args.config][0]))
+
+
+def config_dict(args, n_gpus, pairs_per_gpu, synth, extra=None):
+    res, up, desc = synth.WORKLOADS[args.config]
+    cfg = {"workload": desc, "name": args.config, "res": res, "upsample_res": up,
+           "pairs_per_gpu": pairs_per_gpu, "global_pairs": pairs_per_gpu * n_gpus, "num_samples": 5000,
+           "kde_points": 20000, "homography": "cv2.findHomography(RANSAC, 3 px, 0.99999) restated on the device (adaptive iterations)",
+           "parallelism": f"pairs sharded over {n_gpus} GPU(s); one all_gather_into_tensor of the [steps,B,12] result rows after the last step",
+           "l2": "inputs + outputs per step >> 126 MB L2 (no flush needed)"}
     if extra:
         cfg.update(extra)
     return cfg
 
 
+def pairs_per_gpu(args, world):
+    if args.pairs_per_gpu:
+        return args.pairs_per_gpu
+    base, scaling = CONFIGS[args.config]
+    return max(1, base // world) if scaling == "strong" else base
+
+
+def cpu_reference_run(synth, args, steps, warmup, sample_pairs=1):
+    """The reference's CPU implementation of the path on this box's host cores: its OWN functions where they import
+    (oracle.reference), the oracle port otherwise.  Returns (pairs/s, cpu_baseline dict)."""
+    import torch
+    from oracle import reference as R
+    from oracle.pipeline import cpu_hot_path
+    impl = "reference" if R.available() else "port"
+    if impl == "reference":
+        R.load_reference()                               # import cost outside the timed region
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    res, up, _ = synth.WORKLOADS[args.config]
+    batches = [synth.PairBatch(sample_pairs, res=res, upsample_res=up, num_itr=NUM_ITR, seed=1234, device="cpu", pair_offset=i)
+               for i in range(2)]
+    for w in range(warmup):
+        cpu_hot_path(batches[w % 2], impl=impl)
+    timings = {}
+    t0 = time.perf_counter()
+    for s_ in range(steps):
+        cpu_hot_path(batches[s_ % 2], timings=timings, impl=impl)
+    dt = time.perf_counter() - t0
+    value = sample_pairs * steps / dt
+    what = ("the reference's own local_correlation / GFNet.corr_volume / pos_embed / sample (kde) imported from "
+            + R.reference_root() if impl == "reference" else "oracle port of the reference's torch calls")
+    base = {"value": value, "unit": UNIT, "cores": cores, "kind": impl,
+            "sample": f"{sample_pairs} pair per step x {steps} steps of the same workload: {what}; torch {torch.__version__} CPU with "
+                      f"{cores} threads, kde(half=False, down=8) as the reference does on CPU, cv2.findHomography RANSAC",
+            "seconds_by_stage_per_pair": {k: v / (sample_pairs * steps) for k, v in timings.items()}}
+    return value, base, dt
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the path (oracle port of its own torch/cv2 calls) on host cores."""
+    """--impl reference: rank 0 times the reference's CPU path (see cpu_reference_run); other ranks exit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from gfnet_b200 import synth            # data generation only (CPU tensors)
-    from oracle.pipeline import cpu_hot_path
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sample_pairs = 1
-    batches = [synth.PairBatch(sample_pairs, num_itr=NUM_ITR, seed=1234, device="cpu", pair_offset=i) for i in range(2)]
-    for w in range(args.warmup):
-        cpu_hot_path(batches[w % 2])
-    timings = {}
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        cpu_hot_path(batches[s % 2], timings=timings)
-    dt = time.perf_counter() - t0
-    value = sample_pairs * args.steps / dt
-    base = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sample_pairs} pair per step (op batch 2) of the same workload, torch {torch.__version__} CPU with {cores} threads, "
-                      f"kde(half=False, down=8) as the reference does on CPU, cv2.findHomography RANSAC",
-            "seconds_by_stage_per_pair": {k: v / (sample_pairs * args.steps) for k, v in timings.items()}}
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    synth = load_synth()
+    value, base, dt = cpu_reference_run(synth, args, args.steps, args.warmup)
+    ppg = pairs_per_gpu(args, args.gpus)
+    print(json.dumps({"impl": "reference", "metric": metric_name(args, synth), "value": value, "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": config_dict(args.gpus, {"reference_sample_pairs_per_step": sample_pairs}),
+                      "higher_is_better": True, "scaling": CONFIGS[args.config][1], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": config_dict(args, args.gpus, ppg, synth, {"reference_sample_pairs_per_step": 1}),
                       "cpu_baseline": base,
                       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -136,16 +175,17 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    B = PAIRS_PER_GPU
-    batch = synth.PairBatch(B, num_itr=NUM_ITR, seed=1234, device=dev, rank=rank)
+    from gfnet_b200.dist import gather_equal
+    B = pairs_per_gpu(args, world)
+    res, up, _ = synth.WORKLOADS[args.config]
+    batch = synth.PairBatch(B, res=res, upsample_res=up, num_itr=NUM_ITR, seed=1234, device=dev, rank=rank)
     hp = HotPath()
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
-    gathered = [torch.empty((B, 12), device=dev, dtype=torch.float64) for _ in range(world)] if world > 1 else None
+    rows = torch.zeros((max(args.steps, 8), B, 12), device=dev, dtype=torch.float64)     # result rows of every timed step
 
-    def step(b=batch):
+    def step(b=batch, k=0):
         out = hp.run(b, generator=gen)
-        if world > 1:
-            dist.all_gather(gathered, out["result"])
+        rows[k].copy_(out["result"])
         return out
 
     def barrier():
@@ -162,11 +202,15 @@ def run_ours(args):
     hp.timing = []                     # CUDA-event pairs around every local_correlation launch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        out = step()
+    for k in range(args.steps):
+        out = step(k=k)
+    all_rows = gather_equal(rows[:args.steps])      # the path's only collective: once, after the last step
     e1.record()
+    t_host = time.perf_counter() - t_host0          # host time to ISSUE the steps (no sync): launch-bound if ~ device time
     barrier()
+    assert all_rows.shape[0] == world
     clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     lc_ms = sum(a.elapsed_time(b) for (_, a, b) in hp.timing)
@@ -183,7 +227,7 @@ def run_ours(args):
     # ---- end to end: host (pinned) inputs -> device -> path -> host result, every step.
     # Two device-side input sets: while step i computes, the copy engine uploads step i+1's inputs on a second
     # stream (every step's 1.39 GB upload and its [B,12] read-back are inside the timed region).
-    batch_b = synth.PairBatch(B, num_itr=NUM_ITR, seed=1234, device=dev, rank=rank)
+    batch_b = synth.PairBatch(B, res=res, upsample_res=up, num_itr=NUM_ITR, seed=1234, device=dev, rank=rank)
     sets = [(batch, batch.tensors()), (batch_b, batch_b.tensors())]
     pinned = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in sets[0][1]]
     h2d = sum(t.numel() * t.element_size() for t in pinned)
@@ -209,7 +253,7 @@ def run_ours(args):
             k = i & 1
             nxt = upload(k ^ 1, done[k ^ 1]) if i + 1 < n else None
             main_stream.wait_event(ready)
-            o = step(sets[k][0])
+            o = step(sets[k][0], k=i % rows.shape[0])
             res_host[k].copy_(o["result"], non_blocking=True)
             done[k] = torch.cuda.Event()
             done[k].record(main_stream)
@@ -243,36 +287,25 @@ def run_ours(args):
                                "ms_per_step": t_ms}
         achieved = lc_bytes * args.steps / (lc_ms / 1e3) / 1e9 if lc_ms else None
         traffic = None                     # DRAM bytes of the same launches from the committed ncu capture (tools/lc_traffic.py)
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_lc_dram_traffic.json")))["dram_bytes_per_step"]
-        except Exception:
-            pass
-        roofline = {"kernel": "local_correlation: lc_tc2_kernel (+ lc_prep_plan_kernel) at C >= 32, lc_pt_kernel at C = 16; all scales/iterations/passes of a step", "bound": "hbm",
+        if args.config == "visir448" and B == 32:
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_lc_dram_traffic.json")))["dram_bytes_per_step"]
+            except Exception:
+                pass
+        roofline = {"kernel": "local_correlation: lc_tc2_kernel (+ lc_prep_plan_kernel) at C >= 32, lc_rot_kernel at C = 16; all scales/iterations/passes of a step", "bound": "hbm",
                     "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": src, "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"] if achieved else None, "traffic": traffic,
-                    "traffic_source": "profiles/r1_lc_dram_traffic.json (ncu dram__bytes_read+write, all 14 calls of a step)" if traffic else None,
+                    "traffic_source": "profiles/r2_lc_dram_traffic.json (ncu dram__bytes_read+write, all 14 calls of a step)" if traffic else None,
                     "algorithmic_bytes_per_step": lc_bytes, "launches_per_step": n_lc // max(args.steps, 1),
                     "share_of_step": lc_ms / total_ms if total_ms else None, "by_scale": by_scale}
-        # CPU baseline on this box's host cores: bounded sample (1 pair x 2 steps)
+        # CPU baseline on this box's host cores: bounded sample (1 pair x 2 steps) of the reference's own functions
         cpu = None
         if not args.no_cpu_baseline:
-            from oracle.pipeline import cpu_hot_path
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            cb = synth.PairBatch(1, num_itr=NUM_ITR, seed=1234, device="cpu")
-            cpu_hot_path(cb)
-            t0 = time.perf_counter()
-            tm = {}
-            nrep = 2
-            for _ in range(nrep):
-                cpu_hot_path(cb, timings=tm)
-            dt = time.perf_counter() - t0
-            cpu = {"value": nrep / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"1 pair per step x {nrep} steps of the same workload (oracle port of the reference's torch/cv2 calls, {cores} threads)",
-                   "seconds_by_stage_per_pair": {k: v / nrep for k, v in tm.items()}}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config_dict(world),
+            _, cpu, _ = cpu_reference_run(synth, args, 2, 1)
+        line = {"metric": metric_name(args, synth), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": CONFIGS[args.config][1], "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config_dict(args, world, B, synth),
+                "host_issue_ms_per_step": t_host / args.steps * 1e3,
                 "clocks": clocks, "gpu_launches": hp.kernel_launches(batch) * args.steps,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                         "overlap": "upload of step i+1 on a copy stream while step i computes (two device input sets)"},
@@ -289,6 +322,8 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="visir448", choices=sorted(CONFIGS))
+    ap.add_argument("--pairs-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -30,3 +30,14 @@ def gather_results(local_rows, global_pairs=None):
     if global_pairs is not None:
         assert out.shape[0] == global_pairs
     return out
+
+
+def gather_equal(local):
+    """ONE collective for equally sized shards: ``[..., 12]`` rows of every rank -> ``[world, ...]`` on every rank
+    (``all_gather_into_tensor``: no per-rank copy kernels).  The benchmark calls it once after its K steps (SURVEY.md
+    8(e): "a single gather at the very end"), not once per step."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local[None]
+    out = torch.empty((dist.get_world_size(),) + tuple(local.shape), device=local.device, dtype=local.dtype)
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out

@@ -17,6 +17,9 @@ def pyramid_config(res=448, native=False, upsample_res=None):
 
     reference shapes: gfnet_configs/basic.json:20,23-26 (feat_chs [64,32,16,8], num_grid
     [32,32,64,128,256], radius [7,6,4,2,0]); model/network.py:185-198; 560 pass: :326-349 (no scale 16).
+    The reference always runs at 448 (+ 560); ``res`` = 224 / 672 gives the NATIVE pyramids of SURVEY.md 8(d2)
+    (16/28/56/112 with G = 16,16,32,64 and 48/84/168/336 with G = 48,48,96,192: ``num_grid[0] == res / 14`` as
+    model/network.py:548 requires); ``native`` is kept for call-site readability only.
     """
     chans = {16: 64, 8: 64, 4: 32, 2: 16}
     radius = {16: 7, 8: 6, 4: 4, 2: 2}
@@ -113,6 +116,15 @@ def make_matches(H, m, gen, device, sigma=0.002, outlier_frac=0.0):
     if nout:
         bq[:nout] = torch.rand((nout, 2), generator=gen, device=device) * 2 - 1
     return torch.cat((a, bq), 1).float().contiguous()
+
+
+WORKLOADS = {   # BASELINE.json configs 2-4: (res, upsample_res, description)
+    "visir448": (448, 560, "vis_ir.json 448x448 pairs (pass 1 at 448 + upsample pass at 560), num_itr=2, symmetric"),
+    "map224": (224, 280, "map.json googlemap 224x224 pairs, NATIVE pyramid 16/28/56/112 (+ upsample pass at 280 = 1.25 x, the "
+                         "reference's 560/448 ratio), num_itr=2, symmetric"),
+    "map672": (672, 840, "map.json googlemap 672x672 pairs, NATIVE pyramid 48/84/168/336 (+ upsample pass at 840), num_itr=2, "
+                         "symmetric; global match N = 2304"),
+}
 
 
 class PairBatch:
