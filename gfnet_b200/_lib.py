@@ -11,9 +11,10 @@ LIB_PATH = os.path.join(_HERE, "_C", "libgfnet_b200.so")
 
 EXPORTS = [
     "gfb_abi_version", "gfb_strerror", "gfb_device_info", "gfb_local_corr_f32", "gfb_avg_pool2_f32",
-    "gfb_pad_rows_f32", "gfb_debug_local_corr_counters", "gfb_local_corr_tc_workspace_bytes", "gfb_local_corr_tc_f32", "gfb_local_corr_pt_f32",
-    "gfb_local_corr_tc2_workspace_bytes", "gfb_local_corr_tc2_f32", "gfb_debug_local_corr_v2_counters", "gfb_local_corr_tc2_groups", "gfb_local_corr_tc2_prepare_f32",
-    "gfb_local_corr_tc2_run_f32",
+    "gfb_pad_rows_f32", "gfb_local_corr_pt_f32",
+    "gfb_local_corr_tc2_workspace_bytes", "gfb_local_corr_tc2_f32", "gfb_local_corr_tc2_slice_f32", "gfb_local_corr_tc2_groups",
+    "gfb_local_corr_tc2_prepare_f32", "gfb_local_corr_tc2_run_f32",
+    "gfb_debug_local_corr_v2_counters", "gfb_debug_local_corr_tc2_f32", "gfb_debug_local_corr_pt_f32",
     "gfb_global_match_f32", "gfb_pos_embed_f32", "gfb_kde_f32", "gfb_kde_sym_workspace_bytes", "gfb_kde_sym_f32", "gfb_match_postprocess_f32",
     "gfb_sample_keys_f32", "gfb_balance_keys_f32", "gfb_gather_matches_f32", "gfb_topk_workspace_bytes",
     "gfb_topk_desc_f32", "gfb_homography_workspace_bytes", "gfb_homography_f32", "gfb_homography_cv_f32", "gfb_corner_error_f64",
@@ -39,11 +40,11 @@ def _load():
     lib.gfb_strerror.restype = ctypes.c_char_p
     lib.gfb_strerror.argtypes = [i32]
     lib.gfb_device_info.argtypes = [ctypes.POINTER(i32)] * 3
-    lib.gfb_local_corr_f32.argtypes = [vp, vp, vp, vp] + [i32] * 14 + [vp]
-    lib.gfb_local_corr_tc_workspace_bytes.restype = sz
-    lib.gfb_local_corr_tc_workspace_bytes.argtypes = [i32, i32]
-    lib.gfb_local_corr_tc_f32.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp, sz, vp]
+    lib.gfb_local_corr_f32.argtypes = [vp, vp, vp, vp] + [i32] * 13 + [vp]
     lib.gfb_local_corr_pt_f32.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp]
+    lib.gfb_debug_local_corr_pt_f32.argtypes = [vp, vp, vp, vp] + [i32] * 11 + [vp]
+    lib.gfb_local_corr_tc2_slice_f32.argtypes = [vp, vp, vp, vp] + [i32] * 12 + [vp, sz, vp]
+    lib.gfb_debug_local_corr_tc2_f32.argtypes = [vp, vp, vp, vp] + [i32] * 11 + [vp, sz, vp]
     lib.gfb_local_corr_tc2_workspace_bytes.restype = sz
     lib.gfb_local_corr_tc2_workspace_bytes.argtypes = [i32] * 7
     lib.gfb_local_corr_tc2_groups.argtypes = [i32] * 6
@@ -52,7 +53,6 @@ def _load():
     lib.gfb_local_corr_tc2_f32.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp, sz, vp]
     lib.gfb_debug_local_corr_v2_counters.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), i32]
     lib.gfb_pad_rows_f32.argtypes = [vp, vp, i64, i32, i32, vp]
-    lib.gfb_debug_local_corr_counters.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), i32]
     lib.gfb_avg_pool2_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.gfb_global_match_f32.argtypes = [vp, vp, vp, vp] + [i32] * 8 + [vp]
     lib.gfb_pos_embed_f32.argtypes = [vp, vp] + [i32] * 5 + [vp]
@@ -74,12 +74,30 @@ def _load():
     lib.gfb_corner_error_f64.argtypes = [vp, vp, vp, i32, f32, f32, f32, vp]
     for name in EXPORTS:   # getattr raises AttributeError if the library lacks a declared symbol
         if name not in ("gfb_strerror", "gfb_topk_workspace_bytes", "gfb_homography_workspace_bytes",
-                        "gfb_local_corr_tc_workspace_bytes", "gfb_local_corr_tc2_workspace_bytes",
+                        "gfb_local_corr_tc2_workspace_bytes",
                         "gfb_kde_sym_workspace_bytes"):
             getattr(lib, name).restype = i32
-    if lib.gfb_abi_version() != 1:
+    if lib.gfb_abi_version() != 2:
         raise ImportError("libgfnet_b200.so ABI version mismatch; rebuild with `make -C gfnet_b200/csrc`")
     return lib
+
+
+_device_checked = False
+
+
+def require_sm100():
+    """The kernels are sm_100a only (tcgen05 / TMEM / TMA): fail with a clear message on any other GPU instead of a late
+    'no kernel image is available' (checked once, at the first op call that has a CUDA tensor in hand)."""
+    global _device_checked
+    if _device_checked:
+        return
+    sm, major, minor = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    rc = lib.gfb_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor))
+    if rc != 0:
+        raise GfbError(f"gfb_device_info: {lib.gfb_strerror(rc).decode()} (code {rc})")
+    if major.value != 10:
+        raise GfbError(f"gfnet_b200 needs a Blackwell sm_100 GPU (B200); the current device is sm_{major.value}{minor.value}")
+    _device_checked = True
 
 
 lib = _load()
@@ -112,6 +130,7 @@ def require_cuda_f32(name, t, dtype=None):
         raise TypeError(f"{name} must be a torch.Tensor")
     if t.device.type != "cuda":
         raise RuntimeError(f"{name} is on {t.device}: gfnet_b200 runs on CUDA (sm_100a) only and has no CPU path")
+    require_sm100()
     want = dtype or torch.float32
     if t.dtype != want:
         raise TypeError(f"{name} must be {want}, got {t.dtype}")

@@ -11,12 +11,14 @@ struct LcParams {
     const float* flow;
     float* out;
     int B, C, Hs, Ws, G, r;
+    int Ctot, c0;              // channel slice: the C channels correlated are c0 .. c0 + C of tensors with Ctot channels
+    int accumulate;            // out += instead of out = (second and later channel slices of one correlation)
     int pitch;                 // floats between rows of f1 (>= Ws)
     int k_total, k_offset;
     int sample_mode, padding_mode;
     float ox0, ox1, oy0, oy1;  // torch.linspace endpoints of the window offsets (fp32)
     float inv_sqrt_c;
-    int debug;                 // profiling aid: bit 0 = skip the multiply-accumulate loop, bit 1 = skip the output stores
+    int debug;                 // profiling aids of the debug entry points only (0 in every production call)
 };
 
 // torch.linspace(start, end, steps)[i] in fp32 (ATen RangeFactories: symmetric evaluation).
@@ -43,9 +45,9 @@ static __device__ float lc_generic_point(const LcParams& p, int b, int k, int gy
         sx = fminf((float)(p.Ws - 1), fmaxf(sx, 0.f));
         sy = fminf((float)(p.Hs - 1), fmaxf(sy, 0.f));
     }
-    const float* f0 = p.f0 + (size_t)b * p.C * gg + (size_t)gy * p.G + gx;
+    const float* f0 = p.f0 + ((size_t)b * p.Ctot + p.c0) * gg + (size_t)gy * p.G + gx;
     const size_t plane = (size_t)p.Hs * p.pitch;
-    const float* f1 = p.f1 + (size_t)b * p.C * plane;
+    const float* f1 = p.f1 + ((size_t)b * p.Ctot + p.c0) * plane;
     float acc = 0.f;
     if (p.sample_mode == 1) {
         float rx = rintf(sx), ry = rintf(sy);

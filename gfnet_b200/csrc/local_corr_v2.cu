@@ -391,13 +391,10 @@ lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::M
         // ================= producer =================
         if (lane == 0) {
             uint32_t q = 0;                                   // ring stages issued
-            long long d_we = 0, d_g = 0, d_tot = clock64();
             int n = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
                 const int slot = n % NTS;
-                const long long c0 = clock64();
                 mbar_wait(&gready[slot], (n / NTS) & 1);
-                d_g += clock64() - c0;
                 const BBox bb = bbox[slot];
                 bbox[slot].mnx = INT_MAX; bbox[slot].mny = INT_MAX; bbox[slot].mxx = INT_MIN; bbox[slot].mxy = INT_MIN;
                 const bool none = bb.mnx == INT_MAX;
@@ -418,19 +415,12 @@ lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::M
                 const uint32_t bytes = (uint32_t)((box_w(bwi) * box_h(bhi) + NT) * sizeof(float));
                 for (int c = 0; c < C; ++c, ++q) {
                     const uint32_t s = q % NBUF;
-                    const long long w0 = clock64();
                     mbar_wait(&empty[s], ((q / NBUF) & 1) ^ 1);
-                    d_we += clock64() - w0;
                     if (p.debug & 2) { mbar_arrive(&full[s]); continue; }
                     mbar_expect_tx(&full[s], bytes);
                     tma_load_3d(ring + s * SLOT, tm, &full[s], X0, Y0, b * C + c);
                     tma_load_3d(ring + s * SLOT + BOXMAX, &tmap0, &full[s], tx * TX, ty * TY, b * C + c);
                 }
-            }
-            if (p.debug & 4) {
-                atomicAdd(&g_v2_stats[4], (unsigned long long)d_we);
-                atomicAdd(&g_v2_stats[5], (unsigned long long)d_g);
-                atomicAdd(&g_v2_stats[7], (unsigned long long)(clock64() - d_tot));
             }
         }
         return;
@@ -740,7 +730,7 @@ __device__ __forceinline__ void st_global_256(uint32_t* ptr, const uint32_t (&v)
 // 16 channels of one position: fp32 NCHW -> [bf16 hi(C) | bf16 lo(C)] position-major
 template <int C>
 __device__ __forceinline__ void prep_unit(const float* __restrict__ x, uint32_t* __restrict__ ws, size_t u,
-                                          int H, int W, int pitch) {
+                                          int H, int W, int pitch, int Ctot, int c0) {
     constexpr int NG = C / 16;
     const size_t npos = (size_t)H * W, plane = (size_t)H * pitch;
     const size_t pos = u % npos;
@@ -748,7 +738,7 @@ __device__ __forceinline__ void prep_unit(const float* __restrict__ x, uint32_t*
     const int g = (int)(t % NG);
     const size_t b = t / NG;
     const int y = (int)(pos / W), xx = (int)(pos - (size_t)y * W);
-    const float* src = x + (b * C + (size_t)g * 16) * plane + (size_t)y * pitch + xx;
+    const float* src = x + (b * Ctot + c0 + (size_t)g * 16) * plane + (size_t)y * pitch + xx;
     float v[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] = __ldg(src + (size_t)e * plane);
@@ -776,8 +766,8 @@ __global__ void __launch_bounds__(256) lc_prep_plan_kernel(const LcParams p, con
         const size_t u0 = (size_t)p.B * (C / 16) * p.G * p.G, u1 = (size_t)p.B * (C / 16) * p.Hs * p.Ws;
         const size_t stride = (size_t)(gridDim.x - nplan) * blockDim.x;
         for (size_t u = (size_t)(blockIdx.x - nplan) * blockDim.x + threadIdx.x; u < u0 + u1; u += stride) {
-            if (u < u0) prep_unit<C>(p.f0, ws0, u, p.G, p.G, p.G);
-            else prep_unit<C>(p.f1, ws1, u - u0, p.Hs, p.Ws, p.pitch);
+            if (u < u0) prep_unit<C>(p.f0, ws0, u, p.G, p.G, p.G, p.Ctot, p.c0);
+            else prep_unit<C>(p.f1, ws1, u - u0, p.Hs, p.Ws, p.pitch, p.Ctot, p.c0);
         }
         return;
     }
@@ -839,6 +829,12 @@ __device__ __forceinline__ void st_stream_pred(float* ptr, float v, bool pred) {
     // no "memory" clobber: the outputs are never read back, and the compiler must stay free to hoist the staging reads
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.f32 [%0], %1;\n\t}"
                  ::"l"(ptr), "f"(v), "r"((int)pred));
+}
+
+// corr of a channel slice: the first slice stores, the following ones add (correlation is linear in the channels)
+__device__ __forceinline__ void out_put(float* ptr, float v, int accumulate) {
+    if (accumulate) v += __ldcs(ptr);
+    __stcs(ptr, v);
 }
 
 // ---- main kernel ---------------------------------------------------------------------------------------------------
@@ -1006,12 +1002,12 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
             float* outp = p.out + ((size_t)b * p.k_total + p.k_offset) * gg + (size_t)gy * G + gx;
             if (d.flags & TF_GATHER) {
                 if (valid)
-                    for (int k = 0; k < KK; ++k) st_stream(outp + (size_t)k * gg, lc_generic_point(p, b, k, gy, gx));
+                    for (int k = 0; k < KK; ++k) out_put(outp + (size_t)k * gg, lc_generic_point(p, b, k, gy, gx), p.accumulate);
                 continue;
             }
             const PointGeom pg = point_geom(p, b, gy, gx, valid, R);
             bool live = pg.live;
-            if (valid && !live)
+            if (valid && !live && !p.accumulate)
                 for (int k = 0; k < KK; ++k) st_stream(outp + (size_t)k * gg, 0.f);
             if (d.flags & TF_EMPTY) continue;
             const int tbw = NBW_FIRST + 8 * d.bwi;                 // this tile's staged row width
@@ -1019,7 +1015,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
             const int off = pg.xb - d.x0 - start;
             if (live && (off < 0 || off + W > LDW)) {      // window outside the warp's TMEM pull: exact gather
                 atomicAdd(&g_v2_stats[1], 1ull);
-                for (int k = 0; k < KK; ++k) st_stream(outp + (size_t)k * gg, lc_generic_point(p, b, k, gy, gx));
+                for (int k = 0; k < KK; ++k) out_put(outp + (size_t)k * gg, lc_generic_point(p, b, k, gy, gx), p.accumulate);
                 live = false;
             }
             const int col0 = live ? off : 0;                       // first staged column this lane reads (col0 + KW <= LDW - 1)
@@ -1044,7 +1040,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                 for (int i = 0; i < KW; ++i) {
                     const float d1 = rowp[(i + 1) * 32];
                     const float h = a0 * d0 + a1 * d1;
-                    if (st) __stcs(p.out + idx, wy0 * hprev[i] + wy1 * h);
+                    if (st) out_put(p.out + idx, wy0 * hprev[i] + wy1 * h, p.accumulate);
                     idx += gg32;
                     hprev[i] = h;
                     d0 = d1;
@@ -1056,7 +1052,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                 unsigned idx = lane_idx + (unsigned)(j - 1) * (KW * gg32);
 #pragma unroll
                 for (int i = 0; i < KW; ++i) {
-                    if (st) __stcs(p.out + idx, wy0 * hprev[i]);
+                    if (st) out_put(p.out + idx, wy0 * hprev[i], p.accumulate);
                     idx += gg32;
                     hprev[i] = 0.f;
                 }
@@ -1245,7 +1241,8 @@ static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size
 using namespace gfb;
 
 static int fill_params(LcParams& p, const float* f0, const float* f1, const float* flow, float* out,
-                       int B, int C, int Hs, int Ws, int f1_pitch, int G, int r, int k_total, int k_offset) {
+                       int B, int C, int Hs, int Ws, int f1_pitch, int G, int r, int k_total, int k_offset,
+                       int Ctot = 0, int c0 = 0, int accumulate = 0) {
     GFB_CHECK_ARG(f0 && f1 && flow && out);
     GFB_CHECK_ARG(B > 0 && C > 0 && Hs > 0 && Ws > 0 && G > 0 && r >= 0);
     GFB_CHECK_ARG(f1_pitch == 0 || f1_pitch >= Ws);
@@ -1253,27 +1250,29 @@ static int fill_params(LcParams& p, const float* f0, const float* f1, const floa
     GFB_CHECK_ARG(k_offset >= 0 && k_offset + kk <= k_total);
     p.f0 = f0; p.f1 = f1; p.flow = flow; p.out = out;
     p.B = B; p.C = C; p.Hs = Hs; p.Ws = Ws; p.G = G; p.r = r;
+    p.Ctot = Ctot > 0 ? Ctot : C; p.c0 = c0; p.accumulate = accumulate;
+    GFB_CHECK_ARG(c0 >= 0 && c0 + C <= p.Ctot);
     p.pitch = f1_pitch ? f1_pitch : Ws;
     p.k_total = k_total; p.k_offset = k_offset;
     p.sample_mode = 0; p.padding_mode = 0;
     p.ox0 = (float)(-2.0 * r / Ws); p.ox1 = (float)(2.0 * r / Ws);
     p.oy0 = (float)(-2.0 * r / Hs); p.oy1 = (float)(2.0 * r / Hs);
-    p.inv_sqrt_c = (float)(1.0 / sqrt((double)C));
+    p.inv_sqrt_c = (float)(1.0 / sqrt((double)p.Ctot));
     p.debug = 0;
     return GFB_OK;
 }
 
 // One lattice point per thread (bilinear, zero padding, window offsets in pixels of f1).  f1 rows must be 16-byte
 // multiples apart (f1_pitch % 4 == 0) for the TMA descriptor.
-extern "C" int gfb_local_corr_pt_f32(const float* f0, const float* f1, const float* flow, float* out,
-                                     int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
-                                     int k_total, int k_offset, int tune, gfb_stream_t stream) {
+static int local_corr_pt(const float* f0, const float* f1, const float* flow, float* out,
+                         int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                         int k_total, int k_offset, int tune, int debug, gfb_stream_t stream) {
     LcParams p;
     int rc = fill_params(p, f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset);
     if (rc != GFB_OK) return rc;
+    p.debug = debug;
     if (p.pitch % 4 != 0 || !gfb_aligned(f1, 16)) return GFB_EALIGN;
     if ((size_t)B * C >= (1ull << 31)) return GFB_EUNSUPPORTED;
-    p.debug = tune >> 8; tune &= 255;
     cudaStream_t st = gfb_cu(stream);
     const float s = (float)Ws / (float)G;
     if (!gfb_aligned(f0, 16)) return GFB_EALIGN;
@@ -1299,6 +1298,17 @@ extern "C" int gfb_local_corr_pt_f32(const float* f0, const float* f1, const flo
     return GFB_EUNSUPPORTED;
 }
 
+extern "C" int gfb_local_corr_pt_f32(const float* f0, const float* f1, const float* flow, float* out,
+                                     int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                                     int k_total, int k_offset, int tune, gfb_stream_t stream) {
+    return local_corr_pt(f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset, tune, 0, stream);
+}
+extern "C" int gfb_debug_local_corr_pt_f32(const float* f0, const float* f1, const float* flow, float* out,
+                                           int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                                           int k_total, int k_offset, int tune, int debug, gfb_stream_t stream) {
+    return local_corr_pt(f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset, tune, debug, stream);
+}
+
 extern "C" int gfb_debug_local_corr_v2_counters(unsigned long long* host_out4, int reset) {
     cudaError_t e = cudaSuccess;
     if (host_out4) e = cudaMemcpyFromSymbol(host_out4, lcv2::g_v2_stats, 8 * sizeof(unsigned long long));
@@ -1319,6 +1329,10 @@ extern "C" size_t gfb_local_corr_tc2_workspace_bytes(int B, int C, int Hs, int W
            lcv2::align_up(gb * ws0_per, 1024) + gb * ws1_per;
 }
 
+// (r, C) pairs the tcgen05 kernel is instantiated for: the GFNet scales (4,32) (6,64) (7,64) and the microbench sweep's radii
+#define GFB_TC2_ALL GFB_TC2_CASE(4, 32) GFB_TC2_CASE(6, 64) GFB_TC2_CASE(7, 64) GFB_TC2_CASE(3, 32) GFB_TC2_CASE(5, 64) \
+                    GFB_TC2_CASE(4, 64) GFB_TC2_CASE(2, 64) GFB_TC2_CASE(3, 64) GFB_TC2_CASE(8, 64) GFB_TC2_CASE(2, 32)
+
 // Split form of gfb_local_corr_tc2_f32 for callers that correlate the same feature0 / feature1 against several flows
 // (the iterations of one refiner scale, model/network.py:230-281): prepare once, run per flow.
 extern "C" int gfb_local_corr_tc2_prepare_f32(const float* f0, const float* f1, int B, int C, int Hs, int Ws, int f1_pitch,
@@ -1331,7 +1345,7 @@ extern "C" int gfb_local_corr_tc2_prepare_f32(const float* f0, const float* f1, 
     p.flow = nullptr; p.out = nullptr;
     cudaStream_t st = gfb_cu(stream);
 #define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, 0, 1);
-    GFB_TC2_CASE(4, 32) GFB_TC2_CASE(6, 64) GFB_TC2_CASE(7, 64) GFB_TC2_CASE(3, 32) GFB_TC2_CASE(5, 64) GFB_TC2_CASE(4, 64)
+    GFB_TC2_ALL
 #undef GFB_TC2_CASE
     return GFB_EUNSUPPORTED;
 }
@@ -1345,7 +1359,7 @@ extern "C" int gfb_local_corr_tc2_run_f32(const float* f0, const float* f1, cons
     if (rc != GFB_OK) return rc;
     cudaStream_t st = gfb_cu(stream);
 #define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, 0, 2);
-    GFB_TC2_CASE(4, 32) GFB_TC2_CASE(6, 64) GFB_TC2_CASE(7, 64) GFB_TC2_CASE(3, 32) GFB_TC2_CASE(5, 64) GFB_TC2_CASE(4, 64)
+    GFB_TC2_ALL
 #undef GFB_TC2_CASE
     return GFB_EUNSUPPORTED;
 }
@@ -1358,21 +1372,47 @@ extern "C" int gfb_local_corr_tc2_groups(int B, int C, int Hs, int Ws, int G, in
     return (B + gb - 1) / gb;
 }
 
+// One channel slice of a correlation over Ctot channels: the channels c0 .. c0 + C of feature0 / feature1 ([B,Ctot,...]) are
+// correlated (scaled by 1/sqrt(Ctot)) and stored (accumulate = 0) or added to out (accumulate = 1).  Correlation is linear
+// in the channels, so C-channel kernels cover any Ctot that is a multiple of C (the microbench sweep's C = 128 .. 512).
+extern "C" int gfb_local_corr_tc2_slice_f32(const float* f0, const float* f1, const float* flow, float* out,
+                                            int B, int C, int Ctot, int c0, int accumulate, int Hs, int Ws, int f1_pitch, int G, int r,
+                                            int k_total, int k_offset, void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
+    LcParams p;
+    int rc = fill_params(p, f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset, Ctot, c0, accumulate ? 1 : 0);
+    if (rc != GFB_OK) return rc;
+    cudaStream_t st = gfb_cu(stream);
+#define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, 0);
+    GFB_TC2_ALL
+#undef GFB_TC2_CASE
+    return GFB_EUNSUPPORTED;
+}
+
+static int local_corr_tc2(const float* f0, const float* f1, const float* flow, float* out,
+                          int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                          int k_total, int k_offset, int group, int debug,
+                          void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
+    LcParams p;
+    int rc = fill_params(p, f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset);
+    if (rc != GFB_OK) return rc;
+    GFB_CHECK_ARG(group >= 0 && group <= 255);
+    p.debug = debug;
+    cudaStream_t st = gfb_cu(stream);
+#define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, group);
+    GFB_TC2_ALL
+#undef GFB_TC2_CASE
+    return GFB_EUNSUPPORTED;
+}
+
 extern "C" int gfb_local_corr_tc2_f32(const float* f0, const float* f1, const float* flow, float* out,
                                       int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                                       int k_total, int k_offset, int group,
                                       void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
-    LcParams p;
-    int rc = fill_params(p, f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset);
-    if (rc != GFB_OK) return rc;
-    GFB_CHECK_ARG(group >= 0);
-    p.debug = (group >> 8) & 255;               // profiling aids: bit 0 per-phase clocks of epilogue warp 0 into the debug counters,
-                                               // bit 1 suppress the output stores, bit 2 skip the staging stores, bit 3 skip the B loads,
-                                               // bit 4 skip the MMAs (results are wrong with bits 1-4)
-    group &= 255;
-    cudaStream_t st = gfb_cu(stream);
-#define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, group);
-    GFB_TC2_CASE(4, 32) GFB_TC2_CASE(6, 64) GFB_TC2_CASE(7, 64) GFB_TC2_CASE(3, 32) GFB_TC2_CASE(5, 64) GFB_TC2_CASE(4, 64)
-#undef GFB_TC2_CASE
-    return GFB_EUNSUPPORTED;
+    return local_corr_tc2(f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset, group, 0, workspace, workspace_bytes, stream);
+}
+extern "C" int gfb_debug_local_corr_tc2_f32(const float* f0, const float* f1, const float* flow, float* out,
+                                            int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                                            int k_total, int k_offset, int group, int debug,
+                                            void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
+    return local_corr_tc2(f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset, group, debug & 255, workspace, workspace_bytes, stream);
 }

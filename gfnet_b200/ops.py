@@ -18,26 +18,21 @@ from ._lib import check, lib, ptr, require_cuda_f32, stream_ptr
 _SAMPLE_MODES = {"bilinear": 0, "nearest": 1}
 _PADDING_MODES = {"zeros": 0, "border": 1}
 
-ALGO_AUTO, ALGO_GENERIC, ALGO_STREAM = 0, 1, 2
-# tuning variants (algo = base | variant << 4 | column-divisor override << 8 | quad-row override << 12)
-ALGO_STREAM_P1 = 2 | (1 << 4)       # one lattice point per thread
-ALGO_QUAD_LDS128 = 2 | (8 << 4)     # 4 points per lane, FFMA2, 16-byte aligned segments
-ALGO_QUAD_LDS64 = 2 | (9 << 4)      # same, 8-byte aligned segments
-ALGO_TC = 3                         # tcgen05 banded-GEMM kernel (bf16 hi/lo split); algo = 3 | tune << 4
-
-ALGO_PT = 4                         # one point per thread, whole patch in registers (TMA box per CTA); algo = 4 | tune << 4
+ALGO_AUTO, ALGO_GENERIC = 0, 1
+ALGO_PT = 4                         # one point per thread, whole patch in registers (TMA box per tile); algo = 4 | tune << 4
 ALGO_TC2 = 5                        # tcgen05 banded GEMM fed by TMA from a bf16 hi/lo workspace; algo = 5 | group << 4
 
-_TC_SHAPES = {(2, 16), (4, 32), (6, 64), (7, 64)}   # (r, C) instantiated in csrc/local_corr_tc.cu
-_TC_AUTO = set()                                    # superseded by the TMA-fed kernels below
-_TC2_SHAPES = {(4, 32), (3, 32), (6, 64), (7, 64), (5, 64), (4, 64)}   # csrc/local_corr_v2.cu
+_TC2_SHAPES = {(2, 32), (3, 32), (4, 32), (2, 64), (3, 64), (4, 64), (5, 64), (6, 64), (7, 64), (8, 64)}   # csrc/local_corr_v2.cu
+_TC2_RADII = {32: {2, 3, 4}, 64: {2, 3, 4, 5, 6, 7, 8}}
 _PT_SHAPES = {(2, 16), (4, 32), (1, 16), (1, 8), (2, 8)}
 _PT_AUTO = {(2, 16), (1, 16), (1, 8), (2, 8)}
 
 
-def _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
-    return (win_h == hs and win_w == ws and sample_mode == "bilinear" and padding_mode == "zeros"
-            and (r, c) in _TC_SHAPES)
+def _tc2_slice_channels(r, c):
+    """Channels per slice when C > 64 is served by the 64-channel tcgen05 kernel slice by slice (0 = not served)."""
+    if c > 64 and c % 64 == 0 and r in _TC2_RADII[64]:
+        return 64
+    return 0
 
 
 class PreparedFeatures:
@@ -121,90 +116,64 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
         raise ValueError("out has the wrong shape/layout")
     win_h, win_w = (G, G) if grid_based_correlation else (h, w)
     st = stream_ptr(f0.device)
+    base = int(algo) & 15
+    if base not in (ALGO_AUTO, ALGO_GENERIC, ALGO_PT, ALGO_TC2):
+        raise NotImplementedError(f"local_correlation: unknown algo {algo}")
+
+    def next_level(f1, hs, ws):
+        nxt = torch.empty((B, c, hs // 2, ws // 2), device=f1.device, dtype=f1.dtype)    # local_correlation.py:71: avg_pool2d(2, 2)
+        check(lib.gfb_avg_pool2_f32(ptr(f1), ptr(nxt), B * c, hs, ws, st), "avg_pool2")
+        return nxt
+
     with torch.cuda.device(f0.device):
         for level in range(num_level):
             hs, ws = int(f1.shape[2]), int(f1.shape[3])
-            src, pitch = f1, 0
-            base = int(algo) & 15
-            plain = _tc_eligible_modes(win_h, win_w, hs, ws, sample_mode, padding_mode)
-            if (prepared is not None and level == 0 and num_level == 1 and plain and int(algo) == ALGO_AUTO
-                    and B * kk * G * G < 2 ** 31 and prepared.matches((B, c, h, w), f0, f1, r, G)):
+            plain = win_h == hs and win_w == ws and sample_mode == "bilinear" and padding_mode == "zeros"
+            small = B * kk * num_level * G * G < 2 ** 31          # the tcgen05 kernel indexes its output with 32 bits
+            kt, ko = kk * num_level, kk * level
+            if (prepared is not None and level == 0 and num_level == 1 and plain and base == ALGO_AUTO and small
+                    and prepared.matches((B, c, h, w), f0, f1, r, G)):
                 rc = lib.gfb_local_corr_tc2_run_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r, kk, 0,
                                                     ptr(prepared.wsbuf), prepared.nws, st)
                 check(rc, "local_correlation (tcgen05, prepared features)")
-                continue
-            # (the tcgen05 kernel indexes its output with 32 bits; larger problems stay on the general entry)
-            if base == ALGO_TC2 or (int(algo) == ALGO_AUTO and plain and (r, c) in _TC2_SHAPES
-                                    and B * kk * num_level * G * G < 2 ** 31):
-                if not (plain and (r, c) in _TC2_SHAPES):
+            elif base == ALGO_TC2 or (base == ALGO_AUTO and plain and small and ((r, c) in _TC2_SHAPES or _tc2_slice_channels(r, c))):
+                cs = _tc2_slice_channels(r, c)
+                if not (plain and small and ((r, c) in _TC2_SHAPES or cs)):
                     raise NotImplementedError("local_correlation: the TMA-fed tcgen05 kernel covers bilinear/zeros with "
-                                              f"(r, C) in {sorted(_TC2_SHAPES)}, got r={r}, C={c}")
-                group = int(algo) >> 4 if base == ALGO_TC2 else 0
-                nws = int(lib.gfb_local_corr_tc2_workspace_bytes(B, c, hs, ws, G, r, group & 255))
-                wsbuf = torch.empty(nws, device=f0.device, dtype=torch.uint8)
-                rc = lib.gfb_local_corr_tc2_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r,
-                                                kk * num_level, kk * level, group, ptr(wsbuf), nws, st)
-                check(rc, "local_correlation (tcgen05, TMA-fed)")
-                if level + 1 < num_level:
-                    nxt = torch.empty((B, c, hs // 2, ws // 2), device=f1.device, dtype=f1.dtype)
-                    check(lib.gfb_avg_pool2_f32(ptr(f1), ptr(nxt), B * c, hs, ws, st), "avg_pool2")
-                    f1 = nxt
-                continue
-            if base == ALGO_PT or (int(algo) == ALGO_AUTO and plain and (r, c) in _PT_AUTO and G % 4 == 0):
+                                              f"(r, C) in {sorted(_TC2_SHAPES)} or C a multiple of 64, got r={r}, C={c}")
+                group = (int(algo) >> 4) & 255 if base == ALGO_TC2 else 0
+                if cs:      # C = 128, 256, 512 ...: 64-channel slices, the first stores, the others accumulate
+                    nws = int(lib.gfb_local_corr_tc2_workspace_bytes(B, cs, hs, ws, G, r, 0))
+                    wsbuf = torch.empty(nws, device=f0.device, dtype=torch.uint8)
+                    for c0 in range(0, c, cs):
+                        rc = lib.gfb_local_corr_tc2_slice_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, cs, c, c0, int(c0 > 0), hs, ws, 0,
+                                                              G, r, kt, ko, ptr(wsbuf), nws, st)
+                        check(rc, "local_correlation (tcgen05, channel slice)")
+                else:
+                    nws = int(lib.gfb_local_corr_tc2_workspace_bytes(B, c, hs, ws, G, r, group))
+                    wsbuf = torch.empty(nws, device=f0.device, dtype=torch.uint8)
+                    rc = lib.gfb_local_corr_tc2_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r, kt, ko, group,
+                                                    ptr(wsbuf), nws, st)
+                    check(rc, "local_correlation (tcgen05, TMA-fed)")
+            elif base == ALGO_PT or (base == ALGO_AUTO and plain and (r, c) in _PT_AUTO and G % 4 == 0):
                 if not (plain and (r, c) in _PT_SHAPES):
-                    raise NotImplementedError("local_correlation: the point-per-thread kernel covers bilinear/zeros with "
+                    raise NotImplementedError("local_correlation: the point-per-thread kernels cover bilinear/zeros with "
                                               f"(r, C) in {sorted(_PT_SHAPES)}, got r={r}, C={c}")
-                if ws % 4:
+                src, pitch = f1, 0
+                if ws % 4:      # TMA needs 16-byte global strides: pad each row once (e.g. ws = 70 -> pitch 72)
                     pitch = (ws + 3) // 4 * 4
                     src = torch.empty((B, c, hs, pitch), device=f1.device, dtype=f1.dtype)
                     check(lib.gfb_pad_rows_f32(ptr(f1), ptr(src), B * c * hs, ws, pitch, st), "pad_rows")
-                rc = lib.gfb_local_corr_pt_f32(ptr(f0), ptr(src), ptr(fl), ptr(out), B, c, hs, ws, pitch, G, r,
-                                               kk * num_level, kk * level, int(algo) >> 4 if base == ALGO_PT else 0, st)
+                rc = lib.gfb_local_corr_pt_f32(ptr(f0), ptr(src), ptr(fl), ptr(out), B, c, hs, ws, pitch, G, r, kt, ko,
+                                               (int(algo) >> 4) & 255 if base == ALGO_PT else 0, st)
                 check(rc, "local_correlation (point-per-thread)")
-                if level + 1 < num_level:
-                    nxt = torch.empty((B, c, hs // 2, ws // 2), device=f1.device, dtype=f1.dtype)
-                    check(lib.gfb_avg_pool2_f32(ptr(f1), ptr(nxt), B * c, hs, ws, st), "avg_pool2")
-                    f1 = nxt
-                continue
-            if base == ALGO_TC or (int(algo) == ALGO_AUTO and (r, c) in _TC_AUTO
-                                   and _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode)):
-                if not _tc_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
-                    raise NotImplementedError("local_correlation: the tcgen05 kernel covers bilinear/zeros with (r, C) in "
-                                              f"{sorted(_TC_SHAPES)}, got r={r}, C={c}")
-                nws = int(lib.gfb_local_corr_tc_workspace_bytes(B, G))
-                wsbuf = torch.empty(nws, device=f0.device, dtype=torch.uint8)
-                rc = lib.gfb_local_corr_tc_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r,
-                                               kk * num_level, kk * level, int(algo) >> 4 if base == ALGO_TC else 0,
-                                               ptr(wsbuf), nws, st)
-                check(rc, "local_correlation (tcgen05)")
-                if level + 1 < num_level:
-                    nxt = torch.empty((B, c, hs // 2, ws // 2), device=f1.device, dtype=f1.dtype)
-                    check(lib.gfb_avg_pool2_f32(ptr(f1), ptr(nxt), B * c, hs, ws, st), "avg_pool2")
-                    f1 = nxt
-                continue
-            if ws % 4 and (int(algo) & 15) != ALGO_GENERIC and _stream_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
-                # TMA needs 16-byte global strides: pad each row once (e.g. ws = 70 -> pitch 72)
-                pitch = (ws + 3) // 4 * 4
-                src = torch.empty((B, c, hs, pitch), device=f1.device, dtype=f1.dtype)
-                check(lib.gfb_pad_rows_f32(ptr(f1), ptr(src), B * c * hs, ws, pitch, st), "pad_rows")
-            rc = lib.gfb_local_corr_f32(ptr(f0), ptr(src), ptr(fl), ptr(out), B, c, hs, ws, pitch, G, r, win_h, win_w,
-                                        _SAMPLE_MODES[sample_mode], _PADDING_MODES[padding_mode],
-                                        kk * num_level, kk * level, int(algo), st)
-            check(rc, "local_correlation")
-            if level + 1 < num_level:                      # local_correlation.py:71: avg_pool2d(2, 2)
-                nxt = torch.empty((B, c, hs // 2, ws // 2), device=f1.device, dtype=f1.dtype)
-                check(lib.gfb_avg_pool2_f32(ptr(f1), ptr(nxt), B * c, hs, ws, st), "avg_pool2")
-                f1 = nxt
+            else:
+                rc = lib.gfb_local_corr_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r, win_h, win_w,
+                                            _SAMPLE_MODES[sample_mode], _PADDING_MODES[padding_mode], kt, ko, st)
+                check(rc, "local_correlation")
+            if level + 1 < num_level:
+                f1 = next_level(f1, hs, ws)
     return out
-
-
-def _tc_eligible_modes(win_h, win_w, hs, ws, sample_mode, padding_mode):
-    return win_h == hs and win_w == ws and sample_mode == "bilinear" and padding_mode == "zeros"
-
-
-def _stream_eligible(c, r, win_h, win_w, hs, ws, sample_mode, padding_mode):
-    return (win_h == hs and win_w == ws and sample_mode == "bilinear" and padding_mode == "zeros"
-            and 1 <= r <= 8 and c % 16 == 0 and (c in (16, 32) or c % 64 == 0))
 
 
 def local_correlation_v2_counters(reset=True):
@@ -212,14 +181,6 @@ def local_correlation_v2_counters(reset=True):
     import ctypes
     buf = (ctypes.c_ulonglong * 8)()
     check(lib.gfb_debug_local_corr_v2_counters(buf, int(reset)), "counters")
-    return tuple(int(v) for v in buf)
-
-
-def local_correlation_counters(reset=True):
-    """(tiles, tiles without streamed points, points on the gather path, centred tiles); synchronises."""
-    import ctypes
-    buf = (ctypes.c_ulonglong * 8)()
-    check(lib.gfb_debug_local_corr_counters(buf, int(reset)), "counters")
     return tuple(int(v) for v in buf)
 
 
@@ -333,14 +294,9 @@ def local_correlation_launches(B, c, hs, ws, G, r, calls=1):
         if calls > 1 and groups == 1:
             return 1 + 2 * calls                                              # pre-pass once, then plan + main per flow
         return 2 * groups * calls                                             # fused pre-pass + plan, main kernel
-    return calls * _other_launches(c, r, hs, ws)
-
-
-def _other_launches(c, r, hs, ws):
-    n = 1
-    if ws % 4 and ((r, c) in _PT_AUTO or _stream_eligible(c, r, hs, ws, hs, ws, "bilinear", "zeros")):
-        n += 1                                                                # pad_rows
-    return n
+    if _tc2_slice_channels(r, c):
+        return 2 * (c // 64) * calls
+    return calls * (2 if (ws % 4 and (r, c) in _PT_AUTO) else 1)              # (+ pad_rows)
 
 
 def local_correlation_bytes(B, c, hs, ws, G, r):
@@ -353,5 +309,5 @@ def global_match_flops(B, C, N0, N1):
 
 
 __all__ = ["local_correlation", "kde", "coarse_match", "corr_volume", "pos_embed", "LazyCorrVolume",
-           "local_correlation_bytes", "local_correlation_launches", "local_correlation_prepare", "PreparedFeatures", "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_STREAM", "ALGO_TC",
-           "ALGO_PT", "ALGO_TC2"]
+           "local_correlation_bytes", "local_correlation_launches", "local_correlation_prepare", "PreparedFeatures",
+           "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_PT", "ALGO_TC2"]

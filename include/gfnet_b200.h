@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GFB_ABI_VERSION 1
+#define GFB_ABI_VERSION 2
 
 #define GFB_OK 0
 #define GFB_EINVAL (-1)       /* bad shape / null pointer / bad enum          */
@@ -52,49 +52,42 @@ int gfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *        win_w/win_h = (Ws,Hs) of `featuremap_size` normally, or num_grid when
  *        grid_based_correlation=True (local_correlation.py:33-52).
  *   sample_mode 0 = bilinear, 1 = nearest; padding_mode 0 = zeros, 1 = border; align_corners=False.
- *   algo 0 = auto, 1 = generic gather kernel, 2 = TMA row-streaming kernel (requires
- *        win == (Ws,Hs), bilinear, zeros, C in {16, 32, 64k}, 1 <= r <= 8, pitch % 4 == 0).
- *   f1_pitch: floats between consecutive rows of f1 (0 = Ws).  The TMA kernel needs a pitch that is a
- *        multiple of 4 (16-byte global strides); callers with Ws % 4 != 0 (e.g. 70) pad rows once with
- *        gfb_pad_rows_f32 and pass the padded pitch.
- * num_level > 1 (local_correlation.py:61-71) = one call per level with `gfb_avg_pool2_f32` between. */
+ *   f1_pitch: floats between consecutive rows of f1 (0 = Ws).
+ * This general entry is the per-sample gather kernel (any C, r, mode); the hot kernels for the configuration GFNet uses
+ * are below.  num_level > 1 (local_correlation.py:61-71) = one call per level with `gfb_avg_pool2_f32` between. */
 int gfb_local_corr_f32(const float* f0, const float* f1, const float* flow, float* out,
                        int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                        int win_h, int win_w, int sample_mode, int padding_mode,
-                       int k_total, int k_offset, int algo, gfb_stream_t stream);
-/* Tensor-core variant of gfb_local_corr_f32 for the shapes of the matching pyramid (bilinear, zeros padding,
- * window == (Ws,Hs); (r, C) in {(2,16), (4,32), (6,64), (7,64)}; any Ws/pitch, no alignment requirement).
- * The correlation is a banded GEMM on tcgen05: f0 / f1 are split into bf16 hi + lo on the fly and
- * hi*hi + hi*lo + lo*hi is accumulated in fp32 (relative error ~1e-5, inside the 1e-4 fp32 bar).  Tiles whose
- * windows spread wider than the staged box (wild flow) use exact per-sample gathers.
- *   workspace: >= gfb_local_corr_tc_workspace_bytes(B, G) bytes of device memory (per-tile plan, written by the
- *   call); tune 0 = defaults (bits 0-7 tile columns, 8-11 converter warps, 12-15 accumulator columns / 64).
- * Returns GFB_EUNSUPPORTED for other (r, C): callers then use gfb_local_corr_f32. */
-size_t gfb_local_corr_tc_workspace_bytes(int B, int G);
-int gfb_local_corr_tc_f32(const float* f0, const float* f1, const float* flow, float* out,
-                          int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
-                          int k_total, int k_offset, int tune,
-                          void* workspace, size_t workspace_bytes, gfb_stream_t stream);
-/* Second-generation kernels for the same operator (utils/local_correlation.py:4-72; bilinear, zero padding, window
- * == (Ws,Hs) only -- the configuration GFNet uses, model/network.py:553-554).  Same tensors as gfb_local_corr_f32.
+                       int k_total, int k_offset, gfb_stream_t stream);
+/* Hot kernels for the same operator (utils/local_correlation.py:4-72; bilinear, zero padding, window == (Ws,Hs) only --
+ * the configuration GFNet uses, model/network.py:553-554).  Same tensors as gfb_local_corr_f32.
  *
- * gfb_local_corr_pt_f32: one lattice point per thread, the whole (2r+2)^2 integer patch of dot products in registers,
- *   f1 staged per CTA by one TMA box per 4 channels (zero fill outside the image).  (r, C) in {(2,16), (4,32), (1,16),
- *   (1,8), (2,8)}; f1_pitch % 4 == 0, f0 / f1 16-byte aligned (TMA strides) else GFB_EALIGN; G % 4 == 0 else
- *   GFB_EUNSUPPORTED.  tune 0 = auto box size.
+ * gfb_local_corr_pt_f32: one lattice point per thread, the whole (2r+2)^2 integer patch of dot products in registers, f1
+ *   staged per tile by TMA (zero fill outside the image).  (r, C) = (2,16): lc_rot_kernel (window cells visited in a
+ *   rotated order that makes every shared-memory load bank-conflict free; producer / consumer warps); (4,32), (1,16),
+ *   (1,8), (2,8): lc_pt_kernel.  f1_pitch % 4 == 0, f0 / f1 16-byte aligned (TMA strides) else GFB_EALIGN; G % 4 == 0 else
+ *   GFB_EUNSUPPORTED.  tune 0 = default kernel and box sizes (other values select tilings, see local_corr_v2.cu).
  *
  * gfb_local_corr_tc2_f32: banded GEMM on tcgen05 fed by TMA.  A pre-pass rewrites f0 / f1 once as position-major
- *   rows [bf16 hi(C) | bf16 lo(C)] into `workspace` (processed in groups of `group` batch elements so that the
- *   workspace stays L2-resident; 0 = auto), the main kernel accumulates hi*hi + hi*lo + lo*hi in fp32 (relative error
- *   ~1e-5, inside the 1e-4 fp32 bar).  (r, C) in {(4,32), (3,32), (6,64), (7,64), (5,64), (4,64)}; any Ws / pitch.
- *   workspace >= gfb_local_corr_tc2_workspace_bytes(...) bytes, 128-byte aligned.  Bits 8-15 of `group` are profiling
- *   switches (per-phase clocks, suppress stores / staging / B loads / MMAs / row arithmetic, polling flavours): results
- *   are only valid with those bits clear.
- * Both return GFB_EUNSUPPORTED for other (r, C); points whose windows leave the staged box use the exact gather. */
+ *   rows [bf16 hi(C) | bf16 lo(C)] into `workspace` (processed in groups of `group` batch elements; 0 = auto), the main
+ *   kernel accumulates hi*hi + hi*lo + lo*hi in fp32 (relative error ~1e-5, inside the 1e-4 fp32 bar).
+ *   (r, C) in {(2,32), (3,32), (4,32), (2,64), (3,64), (4,64), (5,64), (6,64), (7,64), (8,64)}; any Ws / pitch.
+ *   workspace >= gfb_local_corr_tc2_workspace_bytes(...) bytes, 128-byte aligned.
+ * gfb_local_corr_tc2_slice_f32: the same kernel on the channel slice [c0, c0 + C) of tensors with Ctot channels, scaled by
+ *   1/sqrt(Ctot), stored (accumulate = 0) or added to out (accumulate = 1): correlation is linear in the channels, so the
+ *   C-channel kernels cover any Ctot that is a multiple of C (C = 128 .. 512 of the microbench sweep).
+ * All return GFB_EUNSUPPORTED for other (r, C); points whose windows leave the staged box use the exact gather. */
 int gfb_local_corr_pt_f32(const float* f0, const float* f1, const float* flow, float* out,
                           int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                           int k_total, int k_offset, int tune, gfb_stream_t stream);
 size_t gfb_local_corr_tc2_workspace_bytes(int B, int C, int Hs, int Ws, int G, int r, int group);
+int gfb_local_corr_tc2_f32(const float* f0, const float* f1, const float* flow, float* out,
+                           int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                           int k_total, int k_offset, int group,
+                           void* workspace, size_t workspace_bytes, gfb_stream_t stream);
+int gfb_local_corr_tc2_slice_f32(const float* f0, const float* f1, const float* flow, float* out,
+                                 int B, int C, int Ctot, int c0, int accumulate, int Hs, int Ws, int f1_pitch, int G, int r,
+                                 int k_total, int k_offset, void* workspace, size_t workspace_bytes, gfb_stream_t stream);
 /* Split form for callers that correlate the same feature0 / feature1 against several flows -- the iterations of one
  * refiner scale (model/network.py:230-281 calls local_correlation num_itr times per scale with unchanged features):
  * `prepare` runs the pre-pass into `workspace` (whole batch in one group, else GFB_EUNSUPPORTED), `run` plans and
@@ -107,22 +100,26 @@ int gfb_local_corr_tc2_run_f32(const float* f0, const float* f1, const float* fl
                                void* workspace, size_t workspace_bytes, gfb_stream_t stream);
 /* how many (pre-pass, main) launch pairs one gfb_local_corr_tc2_f32 call issues for these shapes */
 int gfb_local_corr_tc2_groups(int B, int C, int Hs, int Ws, int G, int group);
-/* Debug aid (synchronises): host_out8 = {lc_pt points on the global-memory path, lc_tc2 points on the gather path,
- * lc_tc2 gather tiles, 0, and -- when the tc2 call had bit 8 of `group` set -- SM clocks epilogue warp 0 of every CTA
- * spent waiting for an accumulator / pulling it out of TMEM / emitting rows, and the chunk count}; reset != 0 zeroes. */
-int gfb_debug_local_corr_v2_counters(unsigned long long* host_out8, int reset);
-int gfb_local_corr_tc2_f32(const float* f0, const float* f1, const float* flow, float* out,
-                           int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
-                           int k_total, int k_offset, int group,
-                           void* workspace, size_t workspace_bytes, gfb_stream_t stream);
 /* F.avg_pool2d(x, 2, 2) on [N,H,W] planes -> [N,H/2,W/2] (local_correlation.py:71). */
 int gfb_avg_pool2_f32(const float* x, float* y, int N, int H, int W, gfb_stream_t stream);
 /* y[rows, pitch] = x[rows, W] with zero fill of the tail of each row. */
 int gfb_pad_rows_f32(const float* x, float* y, long long rows, int W, int pitch, gfb_stream_t stream);
-/* Debug/profiling aid (synchronises!): host_out8[0..3] = tiles launched, tiles without streamed points, lattice
- * points that took the gather path, tiles whose staged box was centred; [4..7] = SM clocks summed over CTAs
- * (set-up, wait for the first row, row loop, tail).  host_out8 may be NULL; reset != 0 zeroes. */
-int gfb_debug_local_corr_counters(unsigned long long* host_out8, int reset);
+/* ---- profiling aids, NOT part of the drop-in surface (results are wrong with any switch set) ----
+ * gfb_debug_local_corr_v2_counters (synchronises): host_out8 = {points on the global-memory path of the point kernels,
+ *   lc_tc2 points on the gather path, lc_tc2 gather tiles, 0, and with debug bit 0 of the tc2 debug entry: SM clocks
+ *   epilogue warp 0 of every CTA spent waiting / pulling TMEM / emitting rows, chunk count}; reset != 0 zeroes.
+ * gfb_debug_local_corr_tc2_f32: gfb_local_corr_tc2_f32 with `debug` switches (bit 0 per-phase clocks, 1 no output stores,
+ *   2 no staging stores, 3 no B loads, 4 no MMAs, 5-7 polling flavours / no row arithmetic).
+ * gfb_debug_local_corr_pt_f32: gfb_local_corr_pt_f32 with `debug` switches for lc_rot_kernel (bit 0 no window reads /
+ *   FMAs, bit 1 no TMA loads). */
+int gfb_debug_local_corr_v2_counters(unsigned long long* host_out8, int reset);
+int gfb_debug_local_corr_tc2_f32(const float* f0, const float* f1, const float* flow, float* out,
+                                 int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                                 int k_total, int k_offset, int group, int debug,
+                                 void* workspace, size_t workspace_bytes, gfb_stream_t stream);
+int gfb_debug_local_corr_pt_f32(const float* f0, const float* f1, const float* flow, float* out,
+                                int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
+                                int k_total, int k_offset, int tune, int debug, gfb_stream_t stream);
 
 /* ---- K2: coarse global match --------------------------------------------------------------
  * replaces GFNet.corr_volume + GFNet.pos_embed, model/network.py:415-440 (call site :251-252).

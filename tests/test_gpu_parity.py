@@ -75,32 +75,83 @@ def test_local_correlation_shapes(gf, shape, kind):
     _close(out, ref)
     gen_out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=1)
     _close(gen_out, ref)
-    for variant in (1, 8, 9):      # P = 1 stream kernel, quad kernel with LDS.128 / LDS.64 segments
-        try:
-            v_out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=2 | (variant << 4))
-        except NotImplementedError:
-            assert variant != 1
-            continue
-        _close(v_out, ref)
 
 
-TC_SHAPES = [s for s in SHAPES if (s[4], s[1]) in {(2, 16), (4, 32), (6, 64), (7, 64)}]
+def _relerr(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max())
 
 
-@pytest.mark.parametrize("shape", TC_SHAPES)
-@pytest.mark.parametrize("kind", ["homography", "adversarial"])
-def test_local_correlation_tcgen05(gf, shape, kind):
-    """tcgen05 banded-GEMM kernel (bf16 hi/lo split, fp32 accumulate) against the oracle, default and tuned tilings."""
+# (shape, bar on max|out - def| / max|def|): the tcgen05 kernels (bf16 hi/lo split, 3 products) are held to 1e-5 against the
+# fp64 definition; the C = 16 point kernel at hs >= 224 to 3e-5: it takes ONE fractional part per lattice point where the
+# reference rounds `flow + offset` per window position in fp32 (~1 ulp of a coordinate of magnitude 1 = 6e-8 normalised
+# = 1.3e-5 px at W = 224), an algorithmic difference the definition (which follows the reference's fp32 coordinates) sees.
+DEF_CASES = [((1, 64, 32, 32, 7), 1e-5), ((1, 64, 56, 32, 6), 1e-5), ((1, 32, 112, 64, 4), 1e-5), ((1, 64, 70, 40, 6), 1e-5),
+             ((1, 32, 140, 80, 4), 1e-5), ((1, 16, 224, 128, 2), 3e-5), ((1, 16, 280, 160, 2), 3e-5)]
+
+
+@pytest.mark.parametrize("case", DEF_CASES)
+def test_local_correlation_hot_kernels_vs_fp64_definition(gf, case):
+    """Separates our arithmetic error from the reference's own fp32 noise: hot kernels against local_correlation_def."""
+    from gfnet_b200 import synth
+    (b, c, hs, G, r), bar = case
+    gen = torch.Generator(device="cuda").manual_seed(31 + hs)
+    cgen = torch.Generator().manual_seed(17)
+    Hs = [synth.random_homography(cgen) for _ in range(b)]
+    f0, f1, flow = synth.scale_inputs(Hs, c, hs, G, gen, "cuda")
+    ref = oracle.local_correlation_def((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
+    port = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
+    out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow)
+    e_ours, e_port = _relerr(out, ref), _relerr(port, ref)
+    print(f"local_correlation {case[0]}: ours vs fp64 definition {e_ours:.2e}, reference operator sequence vs definition {e_port:.2e}")
+    assert e_ours <= bar
+
+
+def test_local_correlation_reference_fixture_real_shapes(gf, golden):
+    """Outputs of the reference's own function at one real pipeline shape per hot kernel (tests/golden/
+    make_golden_real_shapes.py; every 4th lattice row / column stored)."""
+    import importlib.util, os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_real_shapes", os.path.join(here, "golden", "make_golden_real_shapes.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = golden("local_correlation_real")
+    st = int(g["stride"])
+    for i, (c, hs, G, r) in enumerate(mg.SHAPES):
+        f0, f1, flow = mg.real_case(i)
+        chk = np.array([float(f0.double().sum()), float(f1.double().sum()), float(flow.double().sum())])
+        assert np.allclose(chk, g[f"c{i}_checksum"], rtol=1e-9), "input regeneration differs from the fixture's"
+        out = gf.local_correlation((1, c, hs, hs), f0.cuda(), f1.cuda(), r, G, flow=flow.cuda())
+        ref = torch.from_numpy(g[f"c{i}_out"])
+        _close(out[:, :, ::st, ::st], ref, atol_rel=1e-5 if c >= 32 else 4e-5)
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 32, 32, 7), (64, 16, 224, 128, 2)])
+def test_local_correlation_full_batch_vs_oracle_port(gf, shape):
+    """BASELINE config 2's op batch (64) against the oracle port itself (not only against our own gather kernel)."""
     from gfnet_b200 import synth
     b, c, hs, G, r = shape
-    gen = torch.Generator(device="cuda").manual_seed(hash(shape) % 10000 + 1)
-    cgen = torch.Generator().manual_seed(11)
+    gen = torch.Generator(device="cuda").manual_seed(64 + hs)
+    cgen = torch.Generator().manual_seed(23)
     Hs = [synth.random_homography(cgen) for _ in range(b)]
-    f0, f1, flow = synth.scale_inputs(Hs, c, hs, G, gen, "cuda", adversarial=(kind == "adversarial"))
+    f0, f1, flow = synth.scale_inputs(Hs, c, hs, G, gen, "cuda")
+    out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow)
     ref = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
-    for tune in (0, 16, 8, 32 | (4 << 8), (2 << 12) if c < 64 else (4 << 12)):
-        out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=3 | (tune << 4))
-        _close(out, ref)
+    _close(out, ref, atol_rel=1e-5 if c >= 32 else 4e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 32, 32, 7), (1, 256, 56, 32, 6), (1, 512, 28, 16, 4), (2, 128, 84, 48, 8), (1, 64, 28, 28, 2), (1, 64, 32, 18, 3)])
+def test_local_correlation_channel_slices_and_sweep_radii(gf, shape):
+    """C = 128 .. 512 through 64-channel tcgen05 slices (gfb_local_corr_tc2_slice_f32) and the sweep's extra radii."""
+    from gfnet_b200 import synth
+    b, c, hs, G, r = shape
+    gen = torch.Generator(device="cuda").manual_seed(7 + c + r)
+    cgen = torch.Generator().manual_seed(29)
+    Hs = [synth.random_homography(cgen) for _ in range(b)]
+    for adv in (False, True):
+        f0, f1, flow = synth.scale_inputs(Hs, c, hs, G, gen, "cuda", adversarial=adv)
+        ref = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
+        _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow), ref, atol_rel=1e-5)
 
 
 V2_SHAPES = SHAPES + [(3, 16, 224, 128, 2), (1, 16, 96, 96, 2), (1, 32, 100, 50, 4), (3, 64, 70, 40, 6), (1, 64, 84, 48, 6)]
@@ -129,7 +180,7 @@ def test_local_correlation_v2_kernels(gf, shape, kind):
             _close(out, ref)
     if c >= 32:
         for group in (0, 1, 2):
-            _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=ALGO_TC2 | (group << 4)), ref)
+            _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=ALGO_TC2 | (group << 4)), ref, atol_rel=1e-5)
         # hoisted pre-pass: prepare once, correlate two different flows against the same features
         prep = gf.local_correlation_prepare((b, c, hs, hs), f0, f1, r, G)
         assert prep is not None
@@ -163,28 +214,8 @@ def test_local_correlation_full_size_properties(gf, shape):
     assert float(gf.local_correlation((b, c, hs, hs), torch.zeros_like(f0), f1, r, G, flow=flow).abs().max()) == 0.0
 
 
-def test_local_correlation_stream_kernel_is_used(gf):
-    """algo=2 must run the TMA kernel (raises NotImplementedError if the shape is not eligible)."""
-    from gfnet_b200 import synth
-    gen = torch.Generator(device="cuda").manual_seed(1)
-    cgen = torch.Generator().manual_seed(2)
-    for (b, c, hs, G, r) in SHAPES[:4] + SHAPES[5:7]:
-        Hs = [synth.random_homography(cgen) for _ in range(b)]
-        f0, f1, flow = synth.scale_inputs(Hs, c, hs, G, gen, "cuda")
-        out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=2)
-        ref = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=1)
-        _close(out, ref)
-    # ws = 70: rows are padded to a 16-byte pitch so the TMA kernel still applies
-    f0, f1, flow = synth.scale_inputs([synth.random_homography(cgen)], 64, 70, 40, gen, "cuda")
-    _close(gf.local_correlation((1, 64, 70, 70), f0, f1, 6, 40, flow=flow, algo=2),
-           gf.local_correlation((1, 64, 70, 70), f0, f1, 6, 40, flow=flow, algo=1))
-    with pytest.raises(NotImplementedError):   # 24 channels: not a streaming-kernel configuration
-        f0, f1, flow = synth.scale_inputs([synth.random_homography(cgen)], 24, 32, 32, gen, "cuda")
-        gf.local_correlation((1, 24, 32, 32), f0, f1, 6, 32, flow=flow, algo=2)
-
-
 def test_local_correlation_edge_flows(gf):
-    """windows fully outside, exactly on pixel centres, NaN-free zero padding, variants P=1/P=4."""
+    """windows fully outside, exactly on pixel centres, NaN-free zero padding."""
     b, c, hs, G, r = 1, 64, 32, 32, 7
     gen = torch.Generator(device="cuda").manual_seed(3)
     f0 = torch.randn((b, c, G, G), generator=gen, device="cuda")
@@ -194,7 +225,7 @@ def test_local_correlation_edge_flows(gf):
     for shift in (0.0, 2.5, -3.0, 0.999):
         flow = torch.stack((xx + shift, yy - shift), 0)[None].contiguous()
         ref = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
-        for algo in (0, 1, 2, 3, 5, 2 | (1 << 4), 2 | (2 << 4), 2 | (4 << 4), 2 | (8 << 4), 2 | (9 << 4)):
+        for algo in (0, 1, 5):
             _close(gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=algo), ref)
 
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/gfnet_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == names
-    assert _lib.lib.gfb_abi_version() == 1
+    assert _lib.lib.gfb_abi_version() == 2
 
 
 def test_error_strings_and_host_side_validation():
@@ -33,7 +33,7 @@ def test_error_strings_and_host_side_validation():
     assert b"invalid" in lib.gfb_strerror(-1) and b"not supported" in lib.gfb_strerror(-2)
     null = ctypes.c_void_p(0)
     assert lib.gfb_kde_f32(null, null, 1, 10, 4, 1, 0.1, null) == _lib.GFB_EINVAL
-    assert lib.gfb_local_corr_f32(null, null, null, null, *([1] * 14), null) == _lib.GFB_EINVAL
+    assert lib.gfb_local_corr_f32(null, null, null, null, *([1] * 13), null) == _lib.GFB_EINVAL
     assert lib.gfb_topk_workspace_bytes(2, 1000, 100) == 2 * 2 * 5120 * 4
     assert lib.gfb_topk_workspace_bytes(1, 204800, 20000) == 2 * 20480 * 4
     assert lib.gfb_homography_workspace_bytes(3, 5000, 512) >= 3 * 8 + 3 * 512 * 72
@@ -85,4 +85,5 @@ def test_launch_accounting_and_workspace_queries():
     assert lib.gfb_kde_sym_workspace_bytes(32, 20000) >= 32 * 20000 * (8 + 4 + 8 + 16)
     batch = synth.PairBatch(1, num_itr=2, device="cpu")
     assert local_correlation_launches(64, 32, 140, 140, 80, 4, calls=2) == 5    # pre-pass hoisted: 1 + 2 x (plan, main)
-    assert HotPath().kernel_launches(batch) == 46
+    assert HotPath().kernel_launches(batch) == 45          # cv2-faithful solver: one RANSAC kernel (no init launch)
+    assert HotPath(n_hyp=512).kernel_launches(batch) == 46

@@ -12,7 +12,7 @@ import gfnet_b200 as gf
 from gfnet_b200 import synth
 from gfnet_b200.pipeline import HotPath
 
-PEAK_HBM = 6529.7  # GB/s, MEASURED_PEAKS.json
+PEAK_HBM = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))['hbm_gbs']
 
 
 def flush_l2(buf):
@@ -41,7 +41,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--b", type=int, default=64)
     ap.add_argument("--out", default="gpurun_out/kbench.json")
-    ap.add_argument("--variants", default="18,130,146")
+    ap.add_argument("--variants", default="0")
     ap.add_argument("--lc-only", action="store_true")
     ap.add_argument("--no-generic", action="store_true")
     args = ap.parse_args()
@@ -63,12 +63,10 @@ def main():
                                    iters=5 if algo == 1 else 10, flush=flush)
             except NotImplementedError:
                 continue
-            from gfnet_b200.ops import local_correlation_counters, local_correlation_v2_counters
-            local_correlation_counters(reset=True)
+            from gfnet_b200.ops import local_correlation_v2_counters
             local_correlation_v2_counters(reset=True)
             gf.local_correlation((b, c, hs, hs), f0, f1, r, g, flow=flow, algo=algo, out=out)
-            cnt = local_correlation_counters(reset=True)
-            cnt = list(cnt) + list(local_correlation_v2_counters(reset=True))
+            cnt = list(local_correlation_v2_counters(reset=True))
             row = dict(scale=s, c=c, hs=hs, G=g, r=r, algo=algo, ms=med, ms_best=best, GBps=nbytes / med / 1e6, counters=cnt,
                        frac=nbytes / med / 1e6 / PEAK_HBM, fma_T=(b * c * (2 * r + 2) ** 2 * g * g) / med / 1e9)
             res["local_corr"].append(row)
@@ -110,6 +108,8 @@ def main():
     res["other"]["torch_topk_204800_to_20000"] = dict(ms=med, ms_best=best, pairs=Bp)
     # homography
     m = torch.stack([synth.make_matches(Hs[i], 5000, gen, dev, sigma=0.001, outlier_frac=0.1) for i in range(Bp)])
+    med, best = timeit(lambda: gf.estimate_homography(m, 448, 448, 448, 448))
+    res["other"]["homography_cv2_faithful"] = dict(ms=med, ms_best=best, pairs=Bp)
     med, best = timeit(lambda: gf.estimate_homography(m, 448, 448, 448, 448, n_hyp=512))
     res["other"]["homography_ransac512"] = dict(ms=med, ms_best=best, pairs=Bp)
     med, best = timeit(lambda: gf.estimate_homography(m, 448, 448, 448, 448, n_hyp=0))
