@@ -12,6 +12,8 @@ struct LcParams {
     float* out;
     int B, C, Hs, Ws, G, r;
     int Ctot, c0;              // channel slice: the C channels correlated are c0 .. c0 + C of tensors with Ctot channels
+    int f0_ctot;               // channels per batch element of the tensor feature0 lives in (= Ctot unless feature0 is the
+                               // leading channel block of the refiner-input buffer [B, 2C+d+K, G, G], model/network.py:555)
     int accumulate;            // out += instead of out = (second and later channel slices of one correlation)
     int pitch;                 // floats between rows of f1 (>= Ws)
     int k_total, k_offset;
@@ -45,7 +47,7 @@ static __device__ float lc_generic_point(const LcParams& p, int b, int k, int gy
         sx = fminf((float)(p.Ws - 1), fmaxf(sx, 0.f));
         sy = fminf((float)(p.Hs - 1), fmaxf(sy, 0.f));
     }
-    const float* f0 = p.f0 + ((size_t)b * p.Ctot + p.c0) * gg + (size_t)gy * p.G + gx;
+    const float* f0 = p.f0 + ((size_t)b * p.f0_ctot + p.c0) * gg + (size_t)gy * p.G + gx;
     const size_t plane = (size_t)p.Hs * p.pitch;
     const float* f1 = p.f1 + ((size_t)b * p.Ctot + p.c0) * plane;
     float acc = 0.f;

@@ -82,7 +82,7 @@ extern "C" int gfb_local_corr_f32(const float* f0, const float* f1, const float*
     LcParams p;
     p.f0 = f0; p.f1 = f1; p.flow = flow; p.out = out;
     p.B = B; p.C = C; p.Hs = Hs; p.Ws = Ws; p.G = G; p.r = r;
-    p.Ctot = C; p.c0 = 0; p.accumulate = 0;
+    p.Ctot = C; p.c0 = 0; p.accumulate = 0; p.f0_ctot = C;
     p.pitch = f1_pitch ? f1_pitch : Ws;
     p.k_total = k_total; p.k_offset = k_offset;
     p.sample_mode = sample_mode; p.padding_mode = padding_mode;

@@ -85,8 +85,8 @@ template <int R>
 __device__ __noinline__ void lc_point_global(const LcParams& p, int b, int gy, int gx, const PointGeom pg, float* outp) {
     constexpr int W = 2 * R + 2, KW = 2 * R + 1;
     const size_t gg = (size_t)p.G * p.G, plane = (size_t)p.Hs * p.pitch;
-    const float* f0 = p.f0 + (size_t)b * p.C * gg + (size_t)gy * p.G + gx;
-    const float* f1 = p.f1 + (size_t)b * p.C * plane;
+    const float* f0 = p.f0 + ((size_t)b * p.f0_ctot + p.c0) * gg + (size_t)gy * p.G + gx;
+    const float* f1 = p.f1 + ((size_t)b * p.Ctot + p.c0) * plane;
     const float a1 = pg.fx, a0 = 1.f - pg.fx;
     const float wy1 = pg.fy * p.inv_sqrt_c, wy0 = (1.f - pg.fy) * p.inv_sqrt_c;
     float hprev[KW];
@@ -166,7 +166,7 @@ lc_pt_kernel(const LcParams p, const int ntiles, const __grid_constant__ CUtenso
         const uint32_t buf = issued % NBUF;
         mbar_expect_tx(&full[buf], (uint32_t)((STAGE + (g == 0 ? F0SZ : 0)) * sizeof(float)));
         tma_load_3d(ring + buf * STAGE, &tmap1, &full[buf], X0, Y0, b * C + g * CG);
-        if (g == 0) tma_load_3d(f0s + slot * F0SZ, &tmap0, &full[buf], tx * TX, ty * TY, b * C);
+        if (g == 0) tma_load_3d(f0s + slot * F0SZ, &tmap0, &full[buf], tx * TX, ty * TY, b * p.f0_ctot);
         ++issued;
     };
 
@@ -288,7 +288,7 @@ static int launch_pt(const LcParams& p, cudaStream_t st) {
         if (rc != GFB_OK) return rc;
     }
     {
-        uint64_t dims[3] = {(uint64_t)G, (uint64_t)G, (uint64_t)p.B * p.C};
+        uint64_t dims[3] = {(uint64_t)G, (uint64_t)G, (uint64_t)p.B * p.f0_ctot};
         uint64_t strides[2] = {(uint64_t)G * 4, (uint64_t)G * G * 4};
         uint32_t box[3] = {(uint32_t)TX, (uint32_t)TY, (uint32_t)C};
         int rc = gfb_encode_tmap_f32(&tmap0, p.f0, 3, dims, strides, box, 0);
@@ -419,7 +419,7 @@ lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::M
                     if (p.debug & 2) { mbar_arrive(&full[s]); continue; }
                     mbar_expect_tx(&full[s], bytes);
                     tma_load_3d(ring + s * SLOT, tm, &full[s], X0, Y0, b * C + c);
-                    tma_load_3d(ring + s * SLOT + BOXMAX, &tmap0, &full[s], tx * TX, ty * TY, b * C + c);
+                    tma_load_3d(ring + s * SLOT + BOXMAX, &tmap0, &full[s], tx * TX, ty * TY, b * p.f0_ctot + c);
                 }
             }
         }
@@ -608,7 +608,7 @@ static int launch_rot(const LcParams& p, cudaStream_t st) {
             if (rc != GFB_OK) return rc;
         }
     {
-        uint64_t dims[3] = {(uint64_t)G, (uint64_t)G, (uint64_t)p.B * p.C};
+        uint64_t dims[3] = {(uint64_t)G, (uint64_t)G, (uint64_t)p.B * p.f0_ctot};
         uint64_t strides[2] = {(uint64_t)G * 4, (uint64_t)G * G * 4};
         uint32_t box[3] = {(uint32_t)TX, (uint32_t)TY, 1u};
         int rc = gfb_encode_tmap_f32(&tmap0, p.f0, 3, dims, strides, box, 0);
@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(256) lc_prep_plan_kernel(const LcParams p, con
         const size_t u0 = (size_t)p.B * (C / 16) * p.G * p.G, u1 = (size_t)p.B * (C / 16) * p.Hs * p.Ws;
         const size_t stride = (size_t)(gridDim.x - nplan) * blockDim.x;
         for (size_t u = (size_t)(blockIdx.x - nplan) * blockDim.x + threadIdx.x; u < u0 + u1; u += stride) {
-            if (u < u0) prep_unit<C>(p.f0, ws0, u, p.G, p.G, p.G, p.Ctot, p.c0);
+            if (u < u0) prep_unit<C>(p.f0, ws0, u, p.G, p.G, p.G, p.f0_ctot, p.c0);
             else prep_unit<C>(p.f1, ws1, u - u0, p.Hs, p.Ws, p.pitch, p.Ctot, p.c0);
         }
         return;
@@ -1198,8 +1198,8 @@ static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size
     for (int b0 = 0; b0 < p0.B; b0 += gb) {
         LcParams p = p0;
         p.B = min(gb, p0.B - b0);
-        p.f0 = p0.f0 + (size_t)b0 * C * gg;
-        p.f1 = p0.f1 + (size_t)b0 * C * plane;
+        p.f0 = p0.f0 + (size_t)b0 * p0.f0_ctot * gg;
+        p.f1 = p0.f1 + (size_t)b0 * p0.Ctot * plane;
         p.flow = p0.flow ? p0.flow + (size_t)b0 * 2 * gg : nullptr;
         p.out = p0.out ? p0.out + (size_t)b0 * p0.k_total * gg : nullptr;
         c.ntiles = p.B * c.tiles_x * c.tiles_y;
@@ -1250,7 +1250,7 @@ static int fill_params(LcParams& p, const float* f0, const float* f1, const floa
     GFB_CHECK_ARG(k_offset >= 0 && k_offset + kk <= k_total);
     p.f0 = f0; p.f1 = f1; p.flow = flow; p.out = out;
     p.B = B; p.C = C; p.Hs = Hs; p.Ws = Ws; p.G = G; p.r = r;
-    p.Ctot = Ctot > 0 ? Ctot : C; p.c0 = c0; p.accumulate = accumulate;
+    p.Ctot = Ctot > 0 ? Ctot : C; p.c0 = c0; p.accumulate = accumulate; p.f0_ctot = p.Ctot;
     GFB_CHECK_ARG(c0 >= 0 && c0 + C <= p.Ctot);
     p.pitch = f1_pitch ? f1_pitch : Ws;
     p.k_total = k_total; p.k_offset = k_offset;
