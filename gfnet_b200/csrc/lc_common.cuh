@@ -34,6 +34,29 @@ __device__ __forceinline__ float unnormalize(float c, int size) {  // align_corn
     return ((c + 1.f) * (float)size - 1.f) / 2.f;
 }
 
+// flow of one lattice point -> window origin, bilinear weights, liveness (window intersects the image)
+struct PointGeom {
+    int xb, yb;
+    float fx, fy;
+    bool live;
+};
+__device__ __forceinline__ PointGeom point_geom(const LcParams& p, int b, int gy, int gx, bool valid, int R) {
+    PointGeom g;
+    g.xb = 0; g.yb = 0; g.fx = 0.f; g.fy = 0.f; g.live = false;
+    if (!valid) return g;
+    const size_t gg = (size_t)p.G * p.G;
+    const float* fl = p.flow + (size_t)b * 2 * gg + (size_t)gy * p.G + gx;
+    const float sx = unnormalize(__ldg(fl), p.Ws), sy = unnormalize(__ldg(fl + gg), p.Hs);
+    if (fabsf(sx) < 1e6f && fabsf(sy) < 1e6f) {
+        const float x0f = floorf(sx), y0f = floorf(sy);
+        const int W = 2 * R + 2;
+        g.xb = (int)x0f - R; g.yb = (int)y0f - R;
+        g.fx = sx - x0f; g.fy = sy - y0f;
+        g.live = !(g.xb >= p.Ws || g.xb + W <= 0 || g.yb >= p.Hs || g.yb + W <= 0);
+    }
+    return g;
+}
+
 // One output element with the reference's exact per-sample coordinate arithmetic.
 static __device__ float lc_generic_point(const LcParams& p, int b, int k, int gy, int gx) {
     const int kw = 2 * p.r + 1;

@@ -50,29 +50,6 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
-// flow of one lattice point -> window origin, bilinear weights, liveness (window intersects the image)
-struct PointGeom {
-    int xb, yb;
-    float fx, fy;
-    bool live;
-};
-__device__ __forceinline__ PointGeom point_geom(const LcParams& p, int b, int gy, int gx, bool valid, int R) {
-    PointGeom g;
-    g.xb = 0; g.yb = 0; g.fx = 0.f; g.fy = 0.f; g.live = false;
-    if (!valid) return g;
-    const size_t gg = (size_t)p.G * p.G;
-    const float* fl = p.flow + (size_t)b * 2 * gg + (size_t)gy * p.G + gx;
-    const float sx = unnormalize(__ldg(fl), p.Ws), sy = unnormalize(__ldg(fl + gg), p.Hs);
-    if (fabsf(sx) < 1e6f && fabsf(sy) < 1e6f) {
-        const float x0f = floorf(sx), y0f = floorf(sy);
-        const int W = 2 * R + 2;
-        g.xb = (int)x0f - R; g.yb = (int)y0f - R;
-        g.fx = sx - x0f; g.fy = sy - y0f;
-        g.live = !(g.xb >= p.Ws || g.xb + W <= 0 || g.yb >= p.Hs || g.yb + W <= 0);
-    }
-    return g;
-}
-
 // debug counters (gfb_debug_local_corr_v2_counters): [0] lc_pt points on the global-memory path, [1] lc_tc2 points on
 // the gather path, [2] lc_tc2 gather tiles
 __device__ unsigned long long g_v2_stats[8];   // [4..7] (debug bit 0): epilogue warp 0 clocks waiting / TMEM pull / rows, chunks
@@ -838,7 +815,7 @@ __device__ __forceinline__ void out_put(float* ptr, float v, int accumulate) {
 }
 
 // ---- main kernel ---------------------------------------------------------------------------------------------------
-template <int R, int C>
+template <int R, int C, bool ACC>      // ACC: out += (second and later channel slices); compile-time so that the store path stays branch-free
 __global__ void __launch_bounds__(TC_THREADS, 2)
 lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan,
               const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ TmapSet tmapB) {
@@ -1040,7 +1017,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                 for (int i = 0; i < KW; ++i) {
                     const float d1 = rowp[(i + 1) * 32];
                     const float h = a0 * d0 + a1 * d1;
-                    if (st) out_put(p.out + idx, wy0 * hprev[i] + wy1 * h, p.accumulate);
+                    if (st) out_put(p.out + idx, wy0 * hprev[i] + wy1 * h, ACC);
                     idx += gg32;
                     hprev[i] = h;
                     d0 = d1;
@@ -1052,7 +1029,7 @@ lc_tc2_kernel(const LcParams p, const TcCfg c, const TileDesc* __restrict__ plan
                 unsigned idx = lane_idx + (unsigned)(j - 1) * (KW * gg32);
 #pragma unroll
                 for (int i = 0; i < KW; ++i) {
-                    if (st) out_put(p.out + idx, wy0 * hprev[i], p.accumulate);
+                    if (st) out_put(p.out + idx, wy0 * hprev[i], ACC);
                     idx += gg32;
                     hprev[i] = 0.f;
                 }
@@ -1190,7 +1167,8 @@ static int launch_tc2(const LcParams& p0, cudaStream_t st, void* workspace, size
 
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    auto kern = lc_tc2_kernel<R, C>;
+    if (p0.accumulate && C != 64) return GFB_EUNSUPPORTED;                     // channel slices are 64 wide
+    auto kern = (C == 64 && p0.accumulate) ? lc_tc2_kernel<R, C, (C == 64)> : lc_tc2_kernel<R, C, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
 

@@ -21,11 +21,20 @@ _PADDING_MODES = {"zeros": 0, "border": 1}
 ALGO_AUTO, ALGO_GENERIC = 0, 1
 ALGO_PT = 4                         # one point per thread, whole patch in registers (TMA box per tile); algo = 4 | tune << 4
 ALGO_TC2 = 5                        # tcgen05 banded GEMM fed by TMA from a bf16 hi/lo workspace; algo = 5 | group << 4
+ALGO_MMA = 6                        # warp-level tensor cores (mma.sync bf16 hi/lo), operands straight from fp32 NCHW; algo = 6 | shape << 4
 
 _TC2_SHAPES = {(2, 32), (3, 32), (4, 32), (2, 64), (3, 64), (4, 64), (5, 64), (6, 64), (7, 64), (8, 64)}   # csrc/local_corr_v2.cu
 _TC2_RADII = {32: {2, 3, 4}, 64: {2, 3, 4, 5, 6, 7, 8}}
 _PT_SHAPES = {(2, 16), (4, 32), (1, 16), (1, 8), (2, 8)}
 _PT_AUTO = {(2, 16), (1, 16), (1, 8), (2, 8)}
+_MMA_SHAPES = {(1, 16), (2, 16), (2, 32), (3, 32), (4, 32)} | {(r, 64) for r in range(2, 9)}            # csrc/local_corr_mma.cu
+# (r, C) the default mode sends to the mma.sync kernel when the caller did not hoist the tcgen05 pre-pass with
+# local_correlation_prepare: one launch instead of pre-pass + plan + main (measured, op batch 64: 0.133 vs 0.167 ms at
+# (32,112,64,4), 0.193 vs 0.435 ms at (32,140,80,4); the 64-channel shapes stay on the tcgen05 kernel)
+_MMA_AUTO = {(2, 32), (3, 32), (4, 32)}
+import os as _os
+if _os.environ.get("GFB_MMA_AUTO"):  # tuning knob: "4x32,6x64" (radius x channels)
+    _MMA_AUTO = {tuple(int(v) for v in t.split("x")) for t in _os.environ["GFB_MMA_AUTO"].split(",")}
 
 
 def _tc2_slice_channels(r, c):
@@ -33,6 +42,10 @@ def _tc2_slice_channels(r, c):
     if c > 64 and c % 64 == 0 and r in _TC2_RADII[64]:
         return 64
     return 0
+
+
+def _mma_slice_channels(r, c):
+    return 64 if (c > 64 and c % 64 == 0 and (r, 64) in _MMA_SHAPES) else 0
 
 
 class PreparedFeatures:
@@ -117,7 +130,7 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
     win_h, win_w = (G, G) if grid_based_correlation else (h, w)
     st = stream_ptr(f0.device)
     base = int(algo) & 15
-    if base not in (ALGO_AUTO, ALGO_GENERIC, ALGO_PT, ALGO_TC2):
+    if base not in (ALGO_AUTO, ALGO_GENERIC, ALGO_PT, ALGO_TC2, ALGO_MMA):
         raise NotImplementedError(f"local_correlation: unknown algo {algo}")
 
     def next_level(f1, hs, ws):
@@ -136,6 +149,21 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
                 rc = lib.gfb_local_corr_tc2_run_f32(ptr(f0), ptr(f1), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r, kk, 0,
                                                     ptr(prepared.wsbuf), prepared.nws, st)
                 check(rc, "local_correlation (tcgen05, prepared features)")
+            elif base == ALGO_MMA or (base == ALGO_AUTO and plain and small and ((r, c) in _MMA_AUTO or (_mma_slice_channels(r, c) and (r, 64) in _MMA_AUTO))):
+                cs = _mma_slice_channels(r, c)
+                if not (plain and small and ((r, c) in _MMA_SHAPES or cs)):
+                    raise NotImplementedError("local_correlation: the mma.sync kernel covers bilinear/zeros with "
+                                              f"(r, C) in {sorted(_MMA_SHAPES)} or C a multiple of 64, got r={r}, C={c}")
+                src, pitch = f1, 0
+                if ws % 4:      # 16-byte cp.async sources: pad each row once (e.g. ws = 70 -> pitch 72)
+                    pitch = (ws + 3) // 4 * 4
+                    src = torch.empty((B, c, hs, pitch), device=f1.device, dtype=f1.dtype)
+                    check(lib.gfb_pad_rows_f32(ptr(f1), ptr(src), B * c * hs, ws, pitch, st), "pad_rows")
+                shape = (int(algo) >> 4) & 255 if base == ALGO_MMA else 0
+                for c0 in range(0, c, cs or c):     # C = 128, 256, 512 ...: 64-channel slices, the first stores, the others accumulate
+                    rc = lib.gfb_local_corr_mma_f32(ptr(f0), ptr(src), ptr(fl), ptr(out), B, cs or c, c, c0, int(c0 > 0), hs, ws, pitch,
+                                                    G, r, kt, ko, shape, st)
+                    check(rc, "local_correlation (mma.sync)")
             elif base == ALGO_TC2 or (base == ALGO_AUTO and plain and small and ((r, c) in _TC2_SHAPES or _tc2_slice_channels(r, c))):
                 cs = _tc2_slice_channels(r, c)
                 if not (plain and small and ((r, c) in _TC2_SHAPES or cs)):
@@ -174,6 +202,14 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
             if level + 1 < num_level:
                 f1 = next_level(f1, hs, ws)
     return out
+
+
+def local_correlation_mma_counters(reset=True):
+    """(points of the mma.sync kernel that took the exact gather, 0, 0, 0); synchronises."""
+    import ctypes
+    buf = (ctypes.c_ulonglong * 4)()
+    check(lib.gfb_debug_local_corr_mma_counters(buf, int(reset)), "counters")
+    return tuple(int(v) for v in buf)
 
 
 def local_correlation_v2_counters(reset=True):
@@ -293,6 +329,8 @@ def local_correlation_launches(B, c, hs, ws, G, r, calls=1):
         groups = int(lib.gfb_local_corr_tc2_groups(B, c, hs, ws, G, 0))
         if calls > 1 and groups == 1:
             return 1 + 2 * calls                                              # pre-pass once, then plan + main per flow
+        if (r, c) in _MMA_AUTO:
+            return calls * (2 if ws % 4 else 1)                               # mma.sync kernel (+ pad_rows)
         return 2 * groups * calls                                             # fused pre-pass + plan, main kernel
     if _tc2_slice_channels(r, c):
         return 2 * (c // 64) * calls
@@ -310,4 +348,4 @@ def global_match_flops(B, C, N0, N1):
 
 __all__ = ["local_correlation", "kde", "coarse_match", "corr_volume", "pos_embed", "LazyCorrVolume",
            "local_correlation_bytes", "local_correlation_launches", "local_correlation_prepare", "PreparedFeatures",
-           "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_PT", "ALGO_TC2"]
+           "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_PT", "ALGO_TC2", "ALGO_MMA"]

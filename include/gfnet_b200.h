@@ -98,6 +98,19 @@ int gfb_local_corr_tc2_run_f32(const float* f0, const float* f1, const float* fl
                                int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
                                int k_total, int k_offset,
                                void* workspace, size_t workspace_bytes, gfb_stream_t stream);
+/* gfb_local_corr_mma_f32: the same operator on the warp-level tensor-core path (mma.sync m16n8k16, bf16 hi/lo split of the
+ *   fp32 operands done in-kernel: hi*hi + hi*lo + lo*hi, fp32 accumulate, relative error ~1e-5) -- reads f0 / f1 / flow as
+ *   they are (fp32 NCHW), no pre-pass, no workspace.  A warp owns 8 x 4 lattice points, the CTA streams the image rows of its
+ *   bounding box through shared memory (cp.async, zero fill), every lane bilerps and stores its own point.
+ *   Channel-slice form like gfb_local_corr_tc2_slice_f32: channels [c0, c0 + C) of tensors with Ctot channels, scaled by
+ *   1/sqrt(Ctot), stored (accumulate = 0) or added (accumulate = 1); Ctot = C (or 0), c0 = 0, accumulate = 0 is the plain
+ *   operator.  (r, C) in {(1,16), (2,16), (2,32), (3,32), (4,32), (2..8, 64)}; f1_pitch % 4 == 0 and f1 16-byte aligned else
+ *   GFB_EALIGN.  shape 0 = auto CTA shape, else warps_x | warps_y << 4 (4|2<<4, 4|1<<4, 2|1<<4).
+ *   gfb_debug_local_corr_mma_counters (synchronises): host_out4[0] = points that took the exact gather. */
+int gfb_local_corr_mma_f32(const float* f0, const float* f1, const float* flow, float* out,
+                           int B, int C, int Ctot, int c0, int accumulate, int Hs, int Ws, int f1_pitch, int G, int r,
+                           int k_total, int k_offset, int shape, gfb_stream_t stream);
+int gfb_debug_local_corr_mma_counters(unsigned long long* host_out4, int reset);
 /* how many (pre-pass, main) launch pairs one gfb_local_corr_tc2_f32 call issues for these shapes */
 int gfb_local_corr_tc2_groups(int B, int C, int Hs, int Ws, int G, int group);
 /* F.avg_pool2d(x, 2, 2) on [N,H,W] planes -> [N,H/2,W/2] (local_correlation.py:71). */
