@@ -7,7 +7,7 @@ Importing this package without the built extension raises ImportError (no fallba
 """
 from . import _lib
 from .ops import (local_correlation, kde, coarse_match, corr_volume, pos_embed, LazyCorrVolume,
-                  local_correlation_bytes, global_match_flops, local_correlation_prepare)
+                  local_correlation_bytes, global_match_flops, local_correlation_prepare, refiner_input)
 from .matcher import match_postprocess, sample, sample_batched, topk_desc, multinomial_from_noise
 from .estimation import (convert_coordinates, estimate_homography, find_homography, corner_error, auc)
 

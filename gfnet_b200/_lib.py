@@ -14,7 +14,7 @@ EXPORTS = [
     "gfb_pad_rows_f32", "gfb_local_corr_pt_f32",
     "gfb_local_corr_tc2_workspace_bytes", "gfb_local_corr_tc2_f32", "gfb_local_corr_tc2_slice_f32", "gfb_local_corr_tc2_groups",
     "gfb_local_corr_tc2_prepare_f32", "gfb_local_corr_tc2_run_f32",
-    "gfb_local_corr_mma_f32", "gfb_debug_local_corr_mma_counters",
+    "gfb_local_corr_mma_f32", "gfb_refiner_assemble_f32", "gfb_local_corr_cat_f32", "gfb_debug_local_corr_mma_counters",
     "gfb_debug_local_corr_v2_counters", "gfb_debug_local_corr_tc2_f32", "gfb_debug_local_corr_pt_f32",
     "gfb_global_match_f32", "gfb_pos_embed_f32", "gfb_kde_f32", "gfb_kde_sym_workspace_bytes", "gfb_kde_sym_f32", "gfb_match_postprocess_f32",
     "gfb_sample_keys_f32", "gfb_balance_keys_f32", "gfb_gather_matches_f32", "gfb_topk_workspace_bytes",
@@ -53,6 +53,8 @@ def _load():
     lib.gfb_local_corr_tc2_run_f32.argtypes = [vp, vp, vp, vp] + [i32] * 9 + [vp, sz, vp]
     lib.gfb_local_corr_tc2_f32.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp, sz, vp]
     lib.gfb_local_corr_mma_f32.argtypes = [vp, vp, vp, vp] + [i32] * 13 + [vp]
+    lib.gfb_refiner_assemble_f32.argtypes = [vp] * 6 + [i32] * 8 + [f32, vp]
+    lib.gfb_local_corr_cat_f32.argtypes = [vp, i32, vp, vp] + [i32] * 9 + [vp, sz, vp]
     lib.gfb_debug_local_corr_mma_counters.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), i32]
     lib.gfb_debug_local_corr_v2_counters.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), i32]
     lib.gfb_pad_rows_f32.argtypes = [vp, vp, i64, i32, i32, vp]

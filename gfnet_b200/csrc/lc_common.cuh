@@ -105,4 +105,8 @@ static __device__ float lc_generic_point(const LcParams& p, int b, int k, int gy
     return acc * p.inv_sqrt_c;
 }
 
+// local_corr_mma.cu: launch the mma.sync kernel on filled parameters (shape 0 = auto CTA shape); GFB_EUNSUPPORTED for (r, C)
+// it is not instantiated for
+int lc_mma_launch(const LcParams& p, int shape, cudaStream_t st);
+
 }  // namespace gfb

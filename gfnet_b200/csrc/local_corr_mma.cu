@@ -390,9 +390,12 @@ extern "C" int gfb_local_corr_mma_f32(const float* f0, const float* f1, const fl
     p.oy0 = (float)(-2.0 * r / Hs); p.oy1 = (float)(2.0 * r / Hs);
     p.inv_sqrt_c = (float)(1.0 / sqrt((double)p.Ctot));
     p.debug = 0;
-    cudaStream_t st = gfb_cu(stream);
-    // CTA shapes: 4 x 2 warps (32 x 8 points, fewest staged bytes per point) where the registers allow two CTAs per SM and
-    // the lattice gives enough tiles; 4 x 1 and 2 x 1 for the 64-channel kernels and small lattices
+    return gfb::lc_mma_launch(p, shape, gfb_cu(stream));
+}
+
+int gfb::lc_mma_launch(const LcParams& p, int shape, cudaStream_t st) {
+    const int r = p.r, C = p.C;
+    // CTA shapes: 4 x 2 warps (32 x 8 points, fewest staged bytes per point), 4 x 1, 2 x 2, 2 x 1
     int nwx = shape & 15, nwy = (shape >> 4) & 15;
     if (shape == 0) {
         // 2 x 1 warps (16 x 4 points) measured fastest on every GFNet shape: the row barrier couples fewer warps and the

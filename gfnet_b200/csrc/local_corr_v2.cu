@@ -1244,13 +1244,14 @@ static int fill_params(LcParams& p, const float* f0, const float* f1, const floa
 // multiples apart (f1_pitch % 4 == 0) for the TMA descriptor.
 static int local_corr_pt(const float* f0, const float* f1, const float* flow, float* out,
                          int B, int C, int Hs, int Ws, int f1_pitch, int G, int r,
-                         int k_total, int k_offset, int tune, int debug, gfb_stream_t stream) {
+                         int k_total, int k_offset, int tune, int debug, gfb_stream_t stream, int f0_ctot = 0) {
     LcParams p;
     int rc = fill_params(p, f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset);
     if (rc != GFB_OK) return rc;
     p.debug = debug;
+    if (f0_ctot) p.f0_ctot = f0_ctot;
     if (p.pitch % 4 != 0 || !gfb_aligned(f1, 16)) return GFB_EALIGN;
-    if ((size_t)B * C >= (1ull << 31)) return GFB_EUNSUPPORTED;
+    if ((size_t)B * p.f0_ctot >= (1ull << 31)) return GFB_EUNSUPPORTED;
     cudaStream_t st = gfb_cu(stream);
     const float s = (float)Ws / (float)G;
     if (!gfb_aligned(f0, 16)) return GFB_EALIGN;
@@ -1393,4 +1394,36 @@ extern "C" int gfb_debug_local_corr_tc2_f32(const float* f0, const float* f1, co
                                             int k_total, int k_offset, int group, int debug,
                                             void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
     return local_corr_tc2(f0, f1, flow, out, B, C, Hs, Ws, f1_pitch, G, r, k_total, k_offset, group, debug & 255, workspace, workspace_bytes, stream);
+}
+
+// ---- local correlation inside the refiner-input buffer (model/network.py:553-555) --------------------------
+// d [B,Dtot,G,G]: feature0 = d[:, 0:C] (written by gfb_refiner_assemble_f32), corr -> d[:, k_offset : k_offset + (2r+1)^2].
+// Dispatch: (r, C) of the point kernels -> gfb_local_corr_pt_f32's kernels; C = 32 -> mma.sync kernel; C = 64 -> tcgen05
+// kernel (phase 0 = pre-pass + plan + main, 1 = pre-pass only, 2 = plan + main on a prepared workspace, as
+// gfb_local_corr_tc2_prepare_f32 / _run_f32; workspace sized by gfb_local_corr_tc2_workspace_bytes) or, without a
+// workspace, the mma.sync kernel.  phase 1 on a shape that needs no pre-pass is a no-op.
+extern "C" int gfb_local_corr_cat_f32(float* d, int Dtot, const float* f1, const float* flow,
+                                      int B, int C, int Hs, int Ws, int f1_pitch, int G, int r, int k_offset,
+                                      int phase, void* workspace, size_t workspace_bytes, gfb_stream_t stream) {
+    GFB_CHECK_ARG(d && Dtot >= C && phase >= 0 && phase <= 2);
+    const bool pt_shape = (r == 2 && C == 16) || (r == 1 && C == 16) || (r == 1 && C == 8) || (r == 2 && C == 8);
+    if (pt_shape && G % 4 == 0) {
+        if (phase == 1) return GFB_OK;
+        return local_corr_pt(d, f1, flow, d, B, C, Hs, Ws, f1_pitch, G, r, Dtot, k_offset, 0, 0, stream, Dtot);
+    }
+    LcParams p;
+    float dummy;
+    int rc = fill_params(p, d, f1, phase == 1 ? &dummy : flow, d, B, C, Hs, Ws, f1_pitch, G, r, Dtot, k_offset);
+    if (rc != GFB_OK) return rc;
+    p.f0_ctot = Dtot;
+    cudaStream_t st = gfb_cu(stream);
+    if (C == 64 && workspace) {
+        if (phase == 1) { p.flow = nullptr; p.out = nullptr; }
+#define GFB_TC2_CASE(RR, CC) if (r == RR && C == CC) return lcv2::launch_tc2<RR, CC>(p, st, workspace, workspace_bytes, 0, phase);
+        GFB_TC2_ALL
+#undef GFB_TC2_CASE
+        return GFB_EUNSUPPORTED;
+    }
+    if (phase == 1) return GFB_OK;
+    return lc_mma_launch(p, 0, st);
 }

@@ -204,6 +204,78 @@ def local_correlation(featuremap_size, feature0, feature1, local_radius, num_gri
     return out
 
 
+def refiner_input(num_grid, x, y, flow, disp_weight, disp_bias, local_radius, scale_factor=1.0, *, out=None, prepared=None,
+                  want_prepared=False, parts=3):
+    """The refiner's input tensor ``d = cat(grid_feature, x_hat, emb_in_displacement, local_corr)`` written in place;
+    reference: ConvRefiner.forward, model/network.py:537-555 (bilinear ``sample_mode``, ``has_displacement_emb`` and
+    ``corr_in_other`` -- the configuration every GFNet scale with a radius uses, :76-135).
+
+    ``x``/``y`` ``[B,c,hs,ws]`` feature maps of image A / B, ``flow [B,2,G,G]``, ``disp_weight [dd,2,1,1]`` / ``disp_bias [dd]``
+    = ``ConvRefiner.disp_emb``.  Returns ``d [B, 2c+dd+(2r+1)^2, G, G]``; ``d[:, :c]`` is ``grid_feature``, ``d[:, -(2r+1)^2:]``
+    the local correlation.  ``prepared`` / ``want_prepared``: the 64-channel scales run the tcgen05 kernel, whose feature
+    pre-pass depends on ``x`` / ``y`` only; pass ``want_prepared=True`` on the first refiner iteration of a scale to get
+    ``(d, handle)`` and hand ``prepared=handle`` (with ``out=d``) to the following ones (model/network.py:257-268).
+    ``parts``: bit 0 = assemble, bit 1 = correlate (bench.py times the two launches separately)."""
+    xx = require_cuda_f32("x", x)
+    yy = require_cuda_f32("y", y)
+    fl = require_cuda_f32("flow", flow)
+    B, c, hs, ws = (int(v) for v in xx.shape)
+    G, r = int(num_grid), int(local_radius)
+    if yy.shape != xx.shape or fl.shape != (B, 2, G, G):
+        raise ValueError("x / y must be [B,c,hs,ws] and flow [B,2,num_grid,num_grid]")
+    w = require_cuda_f32("disp_weight", disp_weight.reshape(disp_weight.shape[0], -1).float())
+    bi = require_cuda_f32("disp_bias", disp_bias.float())
+    dd = int(w.shape[0])
+    if w.shape != (dd, 2) or bi.shape != (dd,):
+        raise ValueError("disp_emb must be a 1x1 convolution 2 -> dd")
+    kk = (2 * r + 1) ** 2
+    dtot = 2 * c + dd + kk
+    if out is None:
+        out = torch.empty((B, dtot, G, G), device=xx.device, dtype=torch.float32)
+    elif out.shape != (B, dtot, G, G) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("out has the wrong shape/layout")
+    st = stream_ptr(xx.device)
+    handle = prepared
+    with torch.cuda.device(xx.device):
+        src, pitch = yy, 0
+        use_tc2 = c == 64 and (r, c) in _TC2_SHAPES and int(lib.gfb_local_corr_tc2_groups(B, c, hs, ws, G, 0)) == 1
+        if ws % 4 and not use_tc2:  # 16-byte row strides for the TMA / cp.async fed kernels: pad each row once
+            if handle is not None:
+                src, pitch = handle["padded"], handle["pitch"]
+            else:
+                pitch = (ws + 3) // 4 * 4
+                src = torch.empty((B, c, hs, pitch), device=yy.device, dtype=yy.dtype)
+                check(lib.gfb_pad_rows_f32(ptr(yy), ptr(src), B * c * hs, ws, pitch, st), "pad_rows")
+        if parts & 1:
+            check(lib.gfb_refiner_assemble_f32(ptr(xx), ptr(yy), ptr(fl), ptr(w), ptr(bi), ptr(out), B, c, hs, ws, 0, G, dd, dtot,
+                                               1.25 * float(scale_factor), st), "refiner_assemble")
+        if parts & 2:
+            wsbuf, nws, phase = None, 0, 0
+            if use_tc2:
+                if handle is not None:
+                    wsbuf, nws, phase = handle["ws"], handle["nws"], 2
+                else:
+                    nws = int(lib.gfb_local_corr_tc2_workspace_bytes(B, c, hs, ws, G, r, 0))
+                    wsbuf = torch.empty(nws, device=xx.device, dtype=torch.uint8)
+            rc = lib.gfb_local_corr_cat_f32(ptr(out), dtot, ptr(src), ptr(fl), B, c, hs, ws, pitch, G, r, 2 * c + dd, phase,
+                                            ptr(wsbuf), nws, st)
+            if rc == _lib.GFB_EUNSUPPORTED:     # any other (r, C): the generic gather kernel, feature0 copied out of d
+                rc = lib.gfb_local_corr_f32(ptr(out[:, :c].contiguous()), ptr(yy), ptr(fl), ptr(out), B, c, hs, ws, 0, G, r, hs, ws,
+                                            0, 0, dtot, 2 * c + dd, st)
+            check(rc, "refiner_input (local correlation)")
+            if handle is None:
+                handle = {"ws": wsbuf, "nws": nws, "padded": src, "pitch": pitch, "x": xx, "y": yy}
+    return (out, handle) if want_prepared else out
+
+
+def refiner_input_launches(B, c, hs, ws, G, r, calls=1):
+    """Kernels `calls` refiner_input calls on the same features launch (assemble + local correlation, pre-pass hoisted)."""
+    n = calls                                                                  # assemble
+    if c == 64 and (r, c) in _TC2_SHAPES and int(lib.gfb_local_corr_tc2_groups(B, c, hs, ws, G, 0)) == 1:
+        return n + 2 + 2 * (calls - 1)                                         # (pre-pass + plan, main), then (plan, main)
+    return n + calls + (1 if ws % 4 else 0)                                    # one kernel per call (+ pad_rows once)
+
+
 def local_correlation_mma_counters(reset=True):
     """(points of the mma.sync kernel that took the exact gather, 0, 0, 0); synchronises."""
     import ctypes
@@ -327,10 +399,10 @@ def local_correlation_launches(B, c, hs, ws, G, r, calls=1):
     with calls > 1 the tcgen05 shapes use ``local_correlation_prepare`` once."""
     if (r, c) in _TC2_SHAPES:
         groups = int(lib.gfb_local_corr_tc2_groups(B, c, hs, ws, G, 0))
-        if calls > 1 and groups == 1:
-            return 1 + 2 * calls                                              # pre-pass once, then plan + main per flow
         if (r, c) in _MMA_AUTO:
             return calls * (2 if ws % 4 else 1)                               # mma.sync kernel (+ pad_rows)
+        if calls > 1 and groups == 1:
+            return 1 + 2 * calls                                              # pre-pass once, then plan + main per flow
         return 2 * groups * calls                                             # fused pre-pass + plan, main kernel
     if _tc2_slice_channels(r, c):
         return 2 * (c // 64) * calls
@@ -347,5 +419,5 @@ def global_match_flops(B, C, N0, N1):
 
 
 __all__ = ["local_correlation", "kde", "coarse_match", "corr_volume", "pos_embed", "LazyCorrVolume",
-           "local_correlation_bytes", "local_correlation_launches", "local_correlation_prepare", "PreparedFeatures",
+           "local_correlation_bytes", "refiner_input", "refiner_input_launches", "local_correlation_launches", "local_correlation_prepare", "PreparedFeatures",
            "global_match_flops", "ALGO_AUTO", "ALGO_GENERIC", "ALGO_PT", "ALGO_TC2", "ALGO_MMA"]

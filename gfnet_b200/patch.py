@@ -4,12 +4,35 @@ The reference binds with ``from utils.kde import kde`` / ``from utils.local_corr
 local_correlation`` (model/network.py:10-11), so the *module attributes of model.network* must be
 replaced, not only utils.*; ``GFNet.corr_volume`` / ``pos_embed`` / ``sample`` are methods.
 """
+import torch
+
 from . import ops, matcher
 
 
-def patch(network_module, utils_local_correlation=None, utils_kde=None):
-    """``patch(model.network)``; returns a dict of the originals so ``unpatch`` can restore them."""
+def _refiner_forward(original):
+    """ConvRefiner.forward (model/network.py:533-564) with lines 537-555 -- the two grid_samples, the displacement
+    embedding, local_correlation and the concatenation -- replaced by ``ops.refiner_input`` (one buffer, written in
+    place); the convolution blocks (:557-562) stay the reference's own modules under the reference's autocast."""
+    def forward(self, num_grid, x, y, flow, scale_factor=1, logits=None):
+        if not (self.has_displacement_emb and self.corr_in_other and self.sample_mode == "bilinear" and x.is_cuda
+                and x.dtype == torch.float32 and y.dtype == torch.float32 and flow.dtype == torch.float32):
+            return original(self, num_grid, x, y, flow, scale_factor=scale_factor, logits=logits)
+        r = self.local_corr_radius
+        d = ops.refiner_input(num_grid, x, y, flow, self.disp_emb.weight, self.disp_emb.bias, r, scale_factor)
+        local_corr = d[:, d.shape[1] - (2 * r + 1) ** 2:]
+        with torch.autocast("cuda", enabled=bool(self.amp), dtype=self.amp_dtype):
+            h = self.block1(d)
+            h = self.hidden_blocks(h)
+        h = self.out_conv(h.float())
+        return h[:, :2], h[:, 2:3], local_corr
+    return forward
+
+
+def patch(network_module, utils_local_correlation=None, utils_kde=None, refiner=True):
+    """``patch(model.network)``; returns a dict of the originals so ``unpatch`` can restore them.  ``refiner=True`` also
+    replaces the input assembly of ``ConvRefiner.forward``."""
     saved = {
+        "refiner_forward": network_module.ConvRefiner.forward,
         "local_correlation": network_module.local_correlation,
         "kde": network_module.kde,
         "corr_volume": network_module.GFNet.corr_volume,
@@ -24,6 +47,8 @@ def patch(network_module, utils_local_correlation=None, utils_kde=None):
     def _sample(self, matches, certainty, num=5000):
         return matcher.sample(matches, certainty, num, sample_mode=self.sample_mode, sample_thresh=self.sample_thresh)
     network_module.GFNet.sample = _sample
+    if refiner:
+        network_module.ConvRefiner.forward = _refiner_forward(saved["refiner_forward"])
     if utils_local_correlation is not None:
         utils_local_correlation.local_correlation = ops.local_correlation
     if utils_kde is not None:
@@ -37,3 +62,4 @@ def unpatch(network_module, saved):
     network_module.GFNet.corr_volume = saved["corr_volume"]
     network_module.GFNet.pos_embed = saved["pos_embed"]
     network_module.GFNet.sample = saved["sample"]
+    network_module.ConvRefiner.forward = saved["refiner_forward"]

@@ -50,7 +50,7 @@ class HotPath:
                     if self.timing is not None:
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         e0.record()
-                    if it == 0 and len(sc["flows"]) > 1:
+                    if it == 0 and len(sc["flows"]) > 1 and (r, c) not in ops._MMA_AUTO:
                         prep = ops.local_correlation_prepare((b, c, hs, hs), sc["f0"], sc["f1"], r, G)
                     ops.local_correlation((b, c, hs, hs), sc["f0"], sc["f1"], r, G, flow=flow, algo=self.lc_algo, out=buf,
                                           prepared=prep)

@@ -193,6 +193,39 @@ def test_local_correlation_v2_kernels(gf, shape, kind):
         _close(gf.local_correlation((b, c, hs, hs), f0b, f1, r, G, flow=flow, prepared=prep), ref)
 
 
+MMA_SHAPES = SHAPES + [(3, 32, 50, 20, 4), (1, 64, 36, 36, 3), (1, 128, 28, 28, 5), (2, 32, 30, 44, 2), (1, 16, 20, 12, 1),
+                       (1, 32, 70, 40, 4), (2, 64, 84, 28, 8)]
+
+
+@pytest.mark.parametrize("shape", MMA_SHAPES)
+@pytest.mark.parametrize("kind", ["homography", "adversarial"])
+def test_local_correlation_mma_kernel(gf, shape, kind):
+    """Warp-level tensor-core kernel (csrc/local_corr_mma.cu: mma.sync bf16 hi/lo, operands straight from fp32 NCHW) against
+    the oracle at every CTA shape; C = 128 runs as two accumulating 64-channel slices; ws % 4 != 0 pads the rows once.
+    Held to the tcgen05 bar (atol 1e-5 * max) where the reference's own coordinate noise allows (maps up to 112 wide)."""
+    from gfnet_b200 import synth
+    from gfnet_b200.ops import ALGO_MMA, local_correlation_mma_counters
+    b, c, hs, G, r = shape
+    gen = torch.Generator(device="cuda").manual_seed(hash(shape) % 10000 + 9)
+    cgen = torch.Generator().manual_seed(23)
+    Hs = [synth.random_homography(cgen) for _ in range(b)]
+    f0, f1, flow = synth.scale_inputs(Hs, c, hs, G, gen, "cuda", adversarial=(kind == "adversarial"))
+    ref = oracle.local_correlation_port((b, c, hs, hs), f0.cpu(), f1.cpu(), r, G, flow=flow.cpu())
+    ran = 0
+    for cta in (0, 2 | 1 << 4, 2 | 2 << 4, 4 | 1 << 4, 4 | 2 << 4):
+        local_correlation_mma_counters(reset=True)
+        try:
+            out = gf.local_correlation((b, c, hs, hs), f0, f1, r, G, flow=flow, algo=ALGO_MMA | (cta << 4))
+        except NotImplementedError:
+            assert cta != 0            # a CTA shape whose staged row would be too wide (or 4 x 2 with 64 channels)
+            continue
+        ran += 1
+        _close(out, ref, atol_rel=1e-5 if hs <= 112 else 4e-5)
+        if kind == "homography" and shape in SHAPES and cta in (0, 2 | 1 << 4):
+            assert local_correlation_mma_counters()[0] == 0, "regular flows of the GFNet shapes must stay on the tensor-core path"
+    assert ran >= 2
+
+
 @pytest.mark.parametrize("shape", [(16, 64, 32, 32, 7), (8, 64, 56, 32, 6), (4, 32, 112, 64, 4), (2, 16, 224, 128, 2),
                                    (8, 64, 70, 40, 6), (4, 32, 140, 80, 4), (2, 16, 280, 160, 2)])
 def test_local_correlation_full_size_properties(gf, shape):
