@@ -132,7 +132,7 @@ def cpu_reference_run(synth, args, steps, warmup, sample_pairs=1):
         cpu_hot_path(batches[s_ % 2], timings=timings, impl=impl)
     dt = time.perf_counter() - t0
     value = sample_pairs * steps / dt
-    what = ("the reference's own local_correlation / GFNet.corr_volume / pos_embed / sample (kde) imported from "
+    what = ("the reference's own local_correlation / GFNet.corr_volume / pos_embed / sample (kde) (+ the torch calls of ConvRefiner.forward :537-555) imported from "
             + R.reference_root() if impl == "reference" else "oracle port of the reference's torch calls")
     base = {"value": value, "unit": UNIT, "cores": cores, "kind": impl,
             "sample": f"{sample_pairs} pair per step x {steps} steps of the same workload: {what}; torch {torch.__version__} CPU with "
@@ -226,7 +226,8 @@ def run_ours(args):
 
     # ---- end to end: host (pinned) inputs -> device -> path -> host result, every step.
     # Two device-side input sets: while step i computes, the copy engine uploads step i+1's inputs on a second
-    # stream (every step's 1.39 GB upload and its [B,12] read-back are inside the timed region).
+    # stream (every step's upload -- feature maps of both images once, flows, logits; the grid features are computed on
+    # the device by the refiner-input assembly -- and its [B,12] read-back are inside the timed region).
     batch_b = synth.PairBatch(B, res=res, upsample_res=up, num_itr=NUM_ITR, seed=1234, device=dev, rank=rank)
     sets = [(batch, batch.tensors()), (batch_b, batch_b.tensors())]
     pinned = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in sets[0][1]]
@@ -253,6 +254,7 @@ def run_ours(args):
             k = i & 1
             nxt = upload(k ^ 1, done[k ^ 1]) if i + 1 < n else None
             main_stream.wait_event(ready)
+            sets[k][0].derive()                        # image-B side of the op batch: device-side concatenation of the uploaded maps
             o = step(sets[k][0], k=i % rows.shape[0])
             res_host[k].copy_(o["result"], non_blocking=True)
             done[k] = torch.cuda.Event()
@@ -292,7 +294,7 @@ def run_ours(args):
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_lc_dram_traffic.json")))["dram_bytes_per_step"]
             except Exception:
                 pass
-        roofline = {"kernel": "local_correlation: lc_tc2_kernel (+ lc_prep_plan_kernel) at C >= 32, lc_rot_kernel at C = 16; all scales/iterations/passes of a step", "bound": "hbm",
+        roofline = {"kernel": "local_correlation: lc_tc2_kernel (+ lc_prep_plan_kernel) at C = 64, lc_mma_kernel at C = 32, lc_rot_kernel at C = 16; all scales/iterations/passes of a step", "bound": "hbm",
                     "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": src, "unit": "GB/s",
                     "frac": achieved / peaks["hbm_gbs"] if achieved else None, "traffic": traffic,
                     "traffic_source": "profiles/r2_lc_dram_traffic.json (ncu dram__bytes_read+write, all 14 calls of a step)" if traffic else None,

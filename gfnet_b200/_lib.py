@@ -53,7 +53,7 @@ def _load():
     lib.gfb_local_corr_tc2_run_f32.argtypes = [vp, vp, vp, vp] + [i32] * 9 + [vp, sz, vp]
     lib.gfb_local_corr_tc2_f32.argtypes = [vp, vp, vp, vp] + [i32] * 10 + [vp, sz, vp]
     lib.gfb_local_corr_mma_f32.argtypes = [vp, vp, vp, vp] + [i32] * 13 + [vp]
-    lib.gfb_refiner_assemble_f32.argtypes = [vp] * 6 + [i32] * 8 + [f32, vp]
+    lib.gfb_refiner_assemble_f32.argtypes = [vp] * 6 + [i32] * 8 + [f32, i32, vp]
     lib.gfb_local_corr_cat_f32.argtypes = [vp, i32, vp, vp] + [i32] * 9 + [vp, sz, vp]
     lib.gfb_debug_local_corr_mma_counters.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), i32]
     lib.gfb_debug_local_corr_v2_counters.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), i32]

@@ -37,14 +37,16 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int Hs, int Ws, in
     return t;
 }
 
-// blockDim = (32, 8): x = lattice column, y = channel slice
-__global__ void __launch_bounds__(256) refiner_assemble_kernel(const float* __restrict__ x, const float* __restrict__ y,
+// One lattice point per thread (blockDim = (32, 4): lanes along gx so that every store is a full 128-byte line), all
+// channels in a loop unrolled four times: 32 independent taps in flight per thread.  HBM-bound: reads x and (through the
+// flow) y once, writes (2C + dd) G^2 floats per batch element.
+__global__ void __launch_bounds__(128) refiner_assemble_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                                const float* __restrict__ flow, const float* __restrict__ w,
                                                                const float* __restrict__ bias, float* __restrict__ d,
                                                                int C, int Hs, int Ws, int y_pitch, int G, int dd, int Dtot,
-                                                               float emb_scale) {
-    const int gx = blockIdx.x * 32 + threadIdx.x, gy = blockIdx.y, b = blockIdx.z;
-    if (gx >= G) return;
+                                                               float emb_scale, int keep_grid) {
+    const int gx = blockIdx.x * 32 + threadIdx.x, gy = blockIdx.y * 4 + threadIdx.y, b = blockIdx.z;
+    if (gx >= G || gy >= G) return;
     const size_t gg = (size_t)G * G;
     const float fx = __ldg(flow + ((size_t)b * 2) * gg + (size_t)gy * G + gx);
     const float fy = __ldg(flow + ((size_t)b * 2 + 1) * gg + (size_t)gy * G + gx);
@@ -52,24 +54,37 @@ __global__ void __launch_bounds__(256) refiner_assemble_kernel(const float* __re
     const float lyn = linspace_at(-1.f + 1.f / (float)G, 1.f - 1.f / (float)G, G, gy);
     const Taps ta = make_taps(lxn, lyn, Hs, Ws, Ws), tb = make_taps(fx, fy, Hs, Ws, y_pitch);
     float* dp = d + (size_t)b * Dtot * gg + (size_t)gy * G + gx;
-    const size_t xplane = (size_t)Hs * Ws, yplane = (size_t)Hs * y_pitch;
+    const unsigned xplane = (unsigned)(Hs * Ws), yplane = (unsigned)(Hs * y_pitch);
     const float* xb = x + (size_t)b * C * xplane;
     const float* yb = y + (size_t)b * C * yplane;
-    for (int c = threadIdx.y; c < C; c += 8) {
-        const float* xp = xb + (size_t)c * xplane;
-        const float* yp = yb + (size_t)c * yplane;
-        float a = 0.f, h = 0.f;
+    if (keep_grid) {            // later refiner iterations of a scale: x has not changed, d[:, 0:C] still holds the grid features
+#pragma unroll 4
+        for (int c = 0; c < C; ++c) {
+            const float* yp = yb + c * yplane;
+            float h = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            a = fmaf(__ldg(xp + ta.o[k]), ta.w[k], a);
-            h = fmaf(__ldg(yp + tb.o[k]), tb.w[k], h);
+            for (int k = 0; k < 4; ++k) h = fmaf(__ldg(yp + tb.o[k]), tb.w[k], h);
+            __stcs(dp + (size_t)(C + c) * gg, h);
         }
-        dp[(size_t)c * gg] = a;
-        dp[(size_t)(C + c) * gg] = h;
+    } else {
+#pragma unroll 4
+        for (int c = 0; c < C; ++c) {
+            const float* xp = xb + c * xplane;
+            const float* yp = yb + c * yplane;
+            float a = 0.f, h = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                a = fmaf(__ldg(xp + ta.o[k]), ta.w[k], a);
+                h = fmaf(__ldg(yp + tb.o[k]), tb.w[k], h);
+            }
+            dp[(size_t)c * gg] = a;          // read again by the correlation kernel: no streaming hint
+            __stcs(dp + (size_t)(C + c) * gg, h);
+        }
     }
     const float vx = emb_scale * (fx - lxn), vy = emb_scale * (fy - lyn);
-    for (int o = threadIdx.y; o < dd; o += 8)
-        dp[(size_t)(2 * C + o) * gg] = fmaf(__ldg(w + 2 * o + 1), vy, fmaf(__ldg(w + 2 * o), vx, __ldg(bias + o)));
+#pragma unroll 4
+    for (int o = 0; o < dd; ++o)
+        __stcs(dp + (size_t)(2 * C + o) * gg, fmaf(__ldg(w + 2 * o + 1), vy, fmaf(__ldg(w + 2 * o), vx, __ldg(bias + o))));
 }
 
 }  // namespace gfb
@@ -77,16 +92,17 @@ __global__ void __launch_bounds__(256) refiner_assemble_kernel(const float* __re
 using namespace gfb;
 
 // x [B,C,Hs,Ws] (image-A feature map), y [B,C,Hs,y_pitch >= Ws] (image-B feature map), flow [B,2,G,G], w [dd,2], bias [dd]
-// -> d[:, 0 : 2C + dd] of d [B,Dtot,G,G].  emb_scale = 40/32 * scale_factor.
+// -> d[:, 0 : 2C + dd] of d [B,Dtot,G,G].  emb_scale = 40/32 * scale_factor.  keep_grid != 0: d[:, 0:C] already holds the grid
+// features of the same x (later refiner iterations of a scale): only x_hat and the embedding are rewritten.
 extern "C" int gfb_refiner_assemble_f32(const float* x, const float* y, const float* flow, const float* w, const float* bias,
                                         float* d, int B, int C, int Hs, int Ws, int y_pitch, int G, int dd, int Dtot,
-                                        float emb_scale, gfb_stream_t stream) {
+                                        float emb_scale, int keep_grid, gfb_stream_t stream) {
     GFB_CHECK_ARG(x && y && flow && d && (dd == 0 || (w && bias)));
     GFB_CHECK_ARG(B > 0 && C > 0 && Hs > 0 && Ws > 0 && G > 0 && dd >= 0 && Dtot >= 2 * C + dd);
     GFB_CHECK_ARG(y_pitch == 0 || y_pitch >= Ws);
-    GFB_CHECK_ARG((size_t)Hs * (y_pitch ? y_pitch : Ws) < (1ull << 31) && B <= 65535 && G <= 65535);
-    dim3 grid((G + 31) / 32, G, B), block(32, 8);
+    GFB_CHECK_ARG((size_t)C * Hs * (y_pitch ? y_pitch : Ws) < (1ull << 31) && B <= 65535 && G <= 65535 * 4);
+    dim3 grid((G + 31) / 32, (G + 3) / 4, B), block(32, 4);
     refiner_assemble_kernel<<<grid, block, 0, gfb_cu(stream)>>>(x, y, flow, w, bias, d, C, Hs, Ws, y_pitch ? y_pitch : Ws, G, dd,
-                                                                  Dtot, emb_scale);
+                                                                  Dtot, emb_scale, keep_grid);
     GFB_LAUNCH_RESULT();
 }

@@ -215,7 +215,8 @@ def refiner_input(num_grid, x, y, flow, disp_weight, disp_bias, local_radius, sc
     the local correlation.  ``prepared`` / ``want_prepared``: the 64-channel scales run the tcgen05 kernel, whose feature
     pre-pass depends on ``x`` / ``y`` only; pass ``want_prepared=True`` on the first refiner iteration of a scale to get
     ``(d, handle)`` and hand ``prepared=handle`` (with ``out=d``) to the following ones (model/network.py:257-268).
-    ``parts``: bit 0 = assemble, bit 1 = correlate (bench.py times the two launches separately)."""
+    ``parts``: bit 0 = assemble, bit 1 = correlate (bench.py times the two launches separately), bit 2 = ``out[:, :c]`` already
+    holds the grid features of this ``x`` (later iterations of a scale: they are not recomputed)."""
     xx = require_cuda_f32("x", x)
     yy = require_cuda_f32("y", y)
     fl = require_cuda_f32("flow", flow)
@@ -237,19 +238,19 @@ def refiner_input(num_grid, x, y, flow, disp_weight, disp_bias, local_radius, sc
     st = stream_ptr(xx.device)
     handle = prepared
     with torch.cuda.device(xx.device):
-        src, pitch = yy, 0
         use_tc2 = c == 64 and (r, c) in _TC2_SHAPES and int(lib.gfb_local_corr_tc2_groups(B, c, hs, ws, G, 0)) == 1
-        if ws % 4 and not use_tc2:  # 16-byte row strides for the TMA / cp.async fed kernels: pad each row once
-            if handle is not None:
-                src, pitch = handle["padded"], handle["pitch"]
-            else:
-                pitch = (ws + 3) // 4 * 4
-                src = torch.empty((B, c, hs, pitch), device=yy.device, dtype=yy.dtype)
-                check(lib.gfb_pad_rows_f32(ptr(yy), ptr(src), B * c * hs, ws, pitch, st), "pad_rows")
         if parts & 1:
             check(lib.gfb_refiner_assemble_f32(ptr(xx), ptr(yy), ptr(fl), ptr(w), ptr(bi), ptr(out), B, c, hs, ws, 0, G, dd, dtot,
-                                               1.25 * float(scale_factor), st), "refiner_assemble")
+                                               1.25 * float(scale_factor), int(bool(parts & 4)), st), "refiner_assemble")
         if parts & 2:
+            src, pitch = yy, 0
+            if ws % 4 and not use_tc2:  # 16-byte row strides for the TMA / cp.async fed kernels: pad each row once
+                if handle is not None:
+                    src, pitch = handle["padded"], handle["pitch"]
+                else:
+                    pitch = (ws + 3) // 4 * 4
+                    src = torch.empty((B, c, hs, pitch), device=yy.device, dtype=yy.dtype)
+                    check(lib.gfb_pad_rows_f32(ptr(yy), ptr(src), B * c * hs, ws, pitch, st), "pad_rows")
             wsbuf, nws, phase = None, 0, 0
             if use_tc2:
                 if handle is not None:

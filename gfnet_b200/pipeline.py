@@ -1,5 +1,7 @@
 """The hot path end to end for a batch of pairs: global match -> local correlation at every scale /
-iteration / pass -> match post-process -> balanced sampling (kde) -> homography -> corner error.
+iteration / pass (as the refiner-input assembly of SURVEY.md 8 f1: grid features, warped features, displacement
+embedding and the correlation written into one buffer) -> match post-process -> balanced sampling (kde) -> homography ->
+corner error.
 
 Order and shapes follow the reference's inference call stack: model/network.py:251-259
 (coarse match, refiner's local_correlation per scale), :326-349 (560 pass), :358-414 (post-process,
@@ -12,9 +14,9 @@ from . import ops, matcher, estimation
 
 
 class HotPath:
-    def __init__(self, num_samples=5000, n_hyp=None, precision=0, lc_algo=0, seed=0):
+    def __init__(self, num_samples=5000, n_hyp=None, precision=0, seed=0):
         # n_hyp None = OpenCV's own RANSAC loop on the device (cv2.findHomography parity), K > 0 = fixed hash-drawn budget
-        self.num_samples, self.n_hyp, self.precision, self.lc_algo, self.seed = num_samples, n_hyp, precision, lc_algo, seed
+        self.num_samples, self.n_hyp, self.precision, self.seed = num_samples, n_hyp, precision, seed
         self._corr = {}
         self.timing = None    # list of (key, start_event, end_event) when bench.py wants per-launch device times
 
@@ -28,10 +30,10 @@ class HotPath:
     def kernel_launches(self, batch):
         """How many of our kernels one run() launches (bench.py's gpu_launches claim)."""
         n = 1                                                   # global match
-        for p in batch.passes:                                  # local_corr: 1 launch (point kernel) or 2 per workspace group
+        for p in batch.passes:                                  # refiner input: assemble + local correlation per iteration
             for sc in p:
                 b = sc["f1"].shape[0]
-                n += ops.local_correlation_launches(b, sc["c"], sc["hs"], sc["hs"], sc["G"], sc["r"], calls=len(sc["flows"]))
+                n += ops.refiner_input_launches(b, sc["c"], sc["hs"], sc["hs"], sc["G"], sc["r"], calls=len(sc["flows"]))
         n += 1 + 1 + 1 + 1 + 5 + 1 + 1 + 1                      # postprocess, keys, topk, gather, kde (keys, sort, gather+boxes, symmetric, finish), balance, topk, gather
         n += (1 if self.n_hyp is None else 2 if self.n_hyp > 0 else 0) + 1 + 1   # (cv ransac | init + ransac), refit, corner error
         return n
@@ -42,18 +44,22 @@ class HotPath:
         for pi, scales in enumerate(batch.passes):
             for sc in scales:
                 b, c, hs, G, r = sc["f1"].shape[0], sc["c"], sc["hs"], sc["G"], sc["r"]
-                # the features of a scale are the same in every refiner iteration (model/network.py:230-281): their
-                # pre-pass is hoisted out of the iteration loop (and timed with the first call)
+                dd = sc["disp_w"].shape[0]
+                # refiner input d = cat(grid_feature, x_hat, emb, local_corr) written in place (model/network.py:537-555);
+                # the features of a scale are the same in every refiner iteration (:230-281), so the tcgen05 pre-pass of
+                # the 64-channel scales is hoisted out of the iteration loop (and timed with the first call)
+                buf = self._corr_buf((pi, sc["scale"]), (b, 2 * c + dd + (2 * r + 1) ** 2, G, G), sc["x"].device)
                 prep = None
                 for it, flow in enumerate(sc["flows"]):
-                    buf = self._corr_buf((pi, sc["scale"]), (b, (2 * r + 1) ** 2, G, G), flow.device)
+                    args = (G, sc["x"], sc["f1"], flow, sc["disp_w"], sc["disp_b"], r, sc["scale_factor"])
+                    ops.refiner_input(*args, out=buf, parts=1 if it == 0 else 5)     # grid features: first iteration only
                     if self.timing is not None:
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         e0.record()
-                    if it == 0 and len(sc["flows"]) > 1 and (r, c) not in ops._MMA_AUTO:
-                        prep = ops.local_correlation_prepare((b, c, hs, hs), sc["f0"], sc["f1"], r, G)
-                    ops.local_correlation((b, c, hs, hs), sc["f0"], sc["f1"], r, G, flow=flow, algo=self.lc_algo, out=buf,
-                                          prepared=prep)
+                    if it == 0:
+                        _, prep = ops.refiner_input(*args, out=buf, parts=2, want_prepared=True)
+                    else:
+                        ops.refiner_input(*args, out=buf, parts=2, prepared=prep)
                     if self.timing is not None:
                         e1.record()
                         self.timing.append((f"pass{pi + 1}_scale{sc['scale']}", e0, e1))

@@ -127,8 +127,30 @@ WORKLOADS = {   # BASELINE.json configs 2-4: (res, upsample_res, description)
 }
 
 
+DISP_DIM = {16: 64, 8: 64, 4: 32, 2: 16}      # gfnet_configs/basic.json:25 displacement_dim (coarse -> fine)
+
+
+def refiner_features(Hn, c, hs, gen, device, noise=0.5):
+    """Feature maps of image A and B of every pair at one scale: B random, A = B warped by the pair's homography
+    (+ noise), so that A(p) correlates with B(H p).  Returns (featA, featB) [B,c,hs,hs]."""
+    B = len(Hn)
+    featB = torch.randn((B, c, hs, hs), generator=gen, device=device)
+    lat = lattice(hs, device)
+    grid = torch.stack([warp_points(torch.as_tensor(h, dtype=torch.float32, device=device), lat) for h in Hn])
+    featA = F.grid_sample(featB, grid.permute(0, 2, 3, 1), mode="bilinear", align_corners=False)
+    featA = featA + noise * torch.randn(featA.shape, generator=gen, device=device)
+    return featA.contiguous(), featB
+
+
 class PairBatch:
-    """All tensors one step of the hot path consumes for B pairs (symmetric => op batch b = 2B)."""
+    """All tensors one step of the hot path consumes for B pairs (symmetric => op batch b = 2B).
+
+    Per scale (reference: model/network.py:213-222 concatenates the two directions, :257-268 runs the refiner):
+    ``x`` [2B,c,hs,hs] = cat(featA, featB) is the image-A side of the op batch (UPLOADED), ``f1`` = cat(featB, featA) the
+    image-B side (``derive()``: a device-side concatenation of the same maps, as the reference does), ``f0`` =
+    grid_sample(x, lattice) the grid features -- what ``ops.refiner_input`` computes on the device; kept here for the CPU
+    arms and the kernel-level tools, never uploaded.  ``disp_w`` / ``disp_b``: random-init ``ConvRefiner.disp_emb``.
+    """
 
     def __init__(self, B, res=448, upsample_res=560, num_itr=1, seed=1234, device="cuda", rank=0,
                  pair_offset=0, native=False):
@@ -144,25 +166,41 @@ class PairBatch:
         for up in ([None, upsample_res] if upsample_res else [None]):
             scales = []
             for (s, c, hs, g, r) in pyramid_config(res, native, up):
-                f0, f1, _ = scale_inputs(Hs, c, hs, g, gen, dev)
+                fa, fb = refiner_features(self.Hn, c, hs, gen, dev)
+                x = torch.cat((fa, fb)).contiguous()
                 flows = [homography_flow(Hs, g, hs, gen, dev) for _ in range(num_itr)]
-                scales.append(dict(scale=s, c=c, hs=hs, G=g, r=r, f0=f0, f1=f1, flows=flows))
+                dd = DISP_DIM[s]
+                scales.append(dict(scale=s, c=c, hs=hs, G=g, r=r, x=x, f1=torch.empty_like(x), f0=None, flows=flows,
+                                   disp_w=(torch.randn((dd, 2), generator=gen, device=dev) * 0.5).contiguous(),
+                                   disp_b=(torch.randn((dd,), generator=gen, device=dev) * 0.1).contiguous(),
+                                   scale_factor=1.0 if up is None else math.sqrt(up * up / float(res * res))))   # network.py:347
             self.passes.append(scales)
-        # coarse features for the global match: the scale-16 maps of pass 1 (full f0 map = grid features there)
+        self.derive(grid_features=True)
+        # coarse features for the global match: the scale-16 maps of pass 1 (num_grid[0] == hs there, so the lattice
+        # samples the pixel centres and the grid features ARE the map)
         s16 = self.passes[0][0]
-        self.coarse_f0, self.coarse_f1 = s16["f0"], s16["f1"]
+        self.coarse_f0, self.coarse_f1 = s16["x"], s16["f1"]
         G = final_grid(res, upsample_res)
         self.G = G
         self.final_flow = homography_flow(Hs, G, G, gen, dev, jitter_px=0.25)
         self.cert_logits = (torch.randn((2 * B, 1, G, G), generator=gen, device=dev) * 2 + 1).contiguous()
 
-    def tensors(self):
-        out = [self.coarse_f0, self.coarse_f1, self.final_flow, self.cert_logits, self.H_gt]
+    def derive(self, grid_features=False):
+        """Image-B side of the op batch from the uploaded maps (in place, same storage every call)."""
+        B = self.B
         for scales in self.passes:
             for sc in scales:
-                out += [sc["f0"], sc["f1"]] + sc["flows"]
-        seen, uniq = set(), []
-        for t in out:
-            if t.data_ptr() not in seen:
-                seen.add(t.data_ptr()); uniq.append(t)
-        return uniq
+                sc["f1"][:B].copy_(sc["x"][B:])
+                sc["f1"][B:].copy_(sc["x"][:B])
+                if grid_features:
+                    lat = lattice(sc["G"], sc["x"].device)[None].expand(2 * B, 2, sc["G"], sc["G"])
+                    sc["f0"] = F.grid_sample(sc["x"], lat.permute(0, 2, 3, 1), mode="bilinear", align_corners=False).contiguous()
+
+    def tensors(self):
+        """What crosses the host boundary every step: feature maps (once per pair and scale), flows, final flow,
+        certainty logits, ground-truth H."""
+        out = [self.final_flow, self.cert_logits, self.H_gt]
+        for scales in self.passes:
+            for sc in scales:
+                out += [sc["x"]] + sc["flows"]
+        return out

@@ -116,14 +116,15 @@ int gfb_debug_local_corr_mma_counters(unsigned long long* host_out4, int reset);
  *   d = cat(grid_sample(x, lattice), grid_sample(y, flow), disp_emb(40/32 * scale_factor * (flow - lattice)),
  *           local_correlation(grid_feature, y, flow))                       d [B, 2C + dd + (2r+1)^2, G, G]
  * gfb_refiner_assemble_f32 writes d[:, 0 : 2C + dd] (bilinear, zeros, align_corners=False like F.grid_sample :537, :547;
- *   the 1x1 conv `disp_emb` :549 as w [dd,2] + bias [dd]; emb_scale = 40/32 * scale_factor); x [B,C,Hs,Ws], y [B,C,Hs,y_pitch].
+ *   the 1x1 conv `disp_emb` :549 as w [dd,2] + bias [dd]; emb_scale = 40/32 * scale_factor); x [B,C,Hs,Ws], y [B,C,Hs,y_pitch];
+ *   keep_grid != 0 leaves d[:, 0:C] as it is (later refiner iterations of one scale: same x, same grid features).
  * gfb_local_corr_cat_f32 correlates feature0 = d[:, 0:C] with f1 along `flow` and writes d[:, k_offset : k_offset + (2r+1)^2]
  *   (the call of :553-554 with its output placed where torch.cat :555 would copy it).  Kernel choice: the point kernels for
  *   their (r, C), the mma.sync kernel for C = 32, the tcgen05 kernel for C = 64 when a workspace is given (phase 0 = one
  *   shot, 1 = pre-pass only, 2 = plan + main on the prepared workspace: the iterations of one scale) else mma.sync. */
 int gfb_refiner_assemble_f32(const float* x, const float* y, const float* flow, const float* w, const float* bias,
                              float* d, int B, int C, int Hs, int Ws, int y_pitch, int G, int dd, int Dtot,
-                             float emb_scale, gfb_stream_t stream);
+                             float emb_scale, int keep_grid, gfb_stream_t stream);
 int gfb_local_corr_cat_f32(float* d, int Dtot, const float* f1, const float* flow,
                            int B, int C, int Hs, int Ws, int f1_pitch, int G, int r, int k_offset,
                            int phase, void* workspace, size_t workspace_bytes, gfb_stream_t stream);

@@ -11,6 +11,7 @@ import time
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from .coarse_match import corr_volume_port, pos_embed_port
 from .local_correlation import local_correlation_port
@@ -43,12 +44,28 @@ def cpu_hot_path(batch, num_samples=5000, seed=0, timings=None, impl="port", noi
     tick("coarse_match", t0)
     t0 = time.perf_counter()
     lc = ref.local_correlation if ref is not None else local_correlation_port
+    t_asm = 0.0
     for scales in batch.passes:
         for sc in scales:
             b, c, hs, G, r = sc["f1"].shape[0], sc["c"], sc["hs"], sc["G"], sc["r"]
             for fl in sc["flows"]:
-                lc((b, c, hs, hs), sc["f0"], sc["f1"], r, G, flow=fl)                                        # network.py:553
-    tick("local_correlation", t0)
+                f0 = sc["f0"]
+                if sc.get("x") is not None:          # refiner input assembly, the torch calls of ConvRefiner.forward :537-555
+                    ta = time.perf_counter()
+                    x_hat = F.grid_sample(sc["f1"], fl.permute(0, 2, 3, 1).contiguous(), align_corners=False, mode="bilinear")
+                    tt = torch.linspace(-1 + 1 / G, 1 - 1 / G, G)
+                    gy, gx = torch.meshgrid((tt, tt), indexing="ij")
+                    coords = torch.stack((gx, gy))[None].expand(b, 2, G, G)
+                    f0 = F.grid_sample(sc["x"], coords.permute(0, 2, 3, 1), align_corners=False, mode="bilinear")
+                    emb = F.conv2d(40 / 32 * sc["scale_factor"] * (fl - coords), sc["disp_w"][:, :, None, None], sc["disp_b"])
+                    t_asm += time.perf_counter() - ta
+                corr = lc((b, c, hs, hs), f0, sc["f1"], r, G, flow=fl)                                       # network.py:553
+                if sc.get("x") is not None:
+                    ta = time.perf_counter()
+                    torch.cat((f0, x_hat, emb, corr), dim=1)                                                 # :555
+                    t_asm += time.perf_counter() - ta
+    t["refiner_assembly"] = t.get("refiner_assembly", 0.0) + t_asm
+    t["local_correlation"] = t.get("local_correlation", 0.0) + time.perf_counter() - t0 - t_asm
     t0 = time.perf_counter()
     warp, cert = match_postprocess_port(batch.final_flow, batch.cert_logits, symmetric=True)                 # :358-384
     tick("match_postprocess", t0)

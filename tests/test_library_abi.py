@@ -85,6 +85,7 @@ def test_launch_accounting_and_workspace_queries():
     assert lib.gfb_local_corr_tc2_workspace_bytes(64, 32, 140, 140, 80, 4, 0) > 64 * (140 * 140 + 80 * 80) * 32 * 4
     assert lib.gfb_kde_sym_workspace_bytes(32, 20000) >= 32 * 20000 * (8 + 4 + 8 + 16)
     batch = synth.PairBatch(1, num_itr=2, device="cpu")
-    assert local_correlation_launches(64, 32, 140, 140, 80, 4, calls=2) == 5    # pre-pass hoisted: 1 + 2 x (plan, main)
-    assert HotPath().kernel_launches(batch) == 45          # cv2-faithful solver: one RANSAC kernel (no init launch)
-    assert HotPath(n_hyp=512).kernel_launches(batch) == 46
+    assert local_correlation_launches(64, 64, 70, 70, 40, 6, calls=2) == 5      # pre-pass hoisted: 1 + 2 x (plan, main)
+    assert local_correlation_launches(64, 32, 140, 140, 80, 4, calls=2) == 2    # mma.sync kernel: one launch per call
+    assert HotPath().kernel_launches(batch) == 50          # 34 refiner-input launches (14 assemble, 20 correlation) + 16; cv2-faithful solver: one RANSAC kernel
+    assert HotPath(n_hyp=512).kernel_launches(batch) == 51

@@ -85,8 +85,9 @@ def test_refiner_input_iterations_reuse_the_prepass(ref):
         first = d.clone()
         again = gf.refiner_input(32, x, y, flow2, cr.disp_emb.weight, cr.disp_emb.bias, 6, out=d, prepared=handle)
         fresh = gf.refiner_input(32, x, y, flow2, cr.disp_emb.weight, cr.disp_emb.bias, 6)
+        kept = gf.refiner_input(32, x, y, flow2, cr.disp_emb.weight, cr.disp_emb.bias, 6, out=d.clone(), prepared=handle, parts=7)
     assert again.data_ptr() == d.data_ptr()
-    assert torch.equal(again, fresh)
+    assert torch.equal(again, fresh) and torch.equal(kept, fresh)      # parts bit 2: grid features of the first call kept
     assert not torch.equal(first, fresh)
 
 
