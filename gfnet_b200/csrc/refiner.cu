@@ -37,16 +37,20 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int Hs, int Ws, in
     return t;
 }
 
-// One lattice point per thread (blockDim = (32, 4): lanes along gx so that every store is a full 128-byte line), all
-// channels in a loop unrolled four times: 32 independent taps in flight per thread.  HBM-bound: reads x and (through the
+// One lattice point per thread, 256 consecutive points (row-major) per block: every store instruction of a block writes
+// 1 KB contiguous per channel plane (DRAM-friendly bursts); all channels in a loop unrolled four times: 32 independent
+// taps in flight per thread.  HBM-bound: reads x and (through the
 // flow) y once, writes (2C + dd) G^2 floats per batch element.
-__global__ void __launch_bounds__(128) refiner_assemble_kernel(const float* __restrict__ x, const float* __restrict__ y,
+__global__ void __launch_bounds__(256) refiner_assemble_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                                const float* __restrict__ flow, const float* __restrict__ w,
                                                                const float* __restrict__ bias, float* __restrict__ d,
                                                                int C, int Hs, int Ws, int y_pitch, int G, int dd, int Dtot,
-                                                               float emb_scale, int keep_grid) {
-    const int gx = blockIdx.x * 32 + threadIdx.x, gy = blockIdx.y * 4 + threadIdx.y, b = blockIdx.z;
-    if (gx >= G || gy >= G) return;
+                                                               float emb_scale, int keep_grid, int cpb) {
+    const int pt = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+    const int c_lo = blockIdx.z * cpb, c_hi = min(C, c_lo + cpb);        // channel group of this block (small lattices: more blocks)
+    const int o_lo = min(dd, c_lo), o_hi = blockIdx.z + 1 == gridDim.z ? dd : min(dd, c_hi);
+    if (pt >= G * G) return;
+    const int gy = pt / G, gx = pt - gy * G;
     const size_t gg = (size_t)G * G;
     const float fx = __ldg(flow + ((size_t)b * 2) * gg + (size_t)gy * G + gx);
     const float fy = __ldg(flow + ((size_t)b * 2 + 1) * gg + (size_t)gy * G + gx);
@@ -57,33 +61,28 @@ __global__ void __launch_bounds__(128) refiner_assemble_kernel(const float* __re
     const unsigned xplane = (unsigned)(Hs * Ws), yplane = (unsigned)(Hs * y_pitch);
     const float* xb = x + (size_t)b * C * xplane;
     const float* yb = y + (size_t)b * C * yplane;
-    if (keep_grid) {            // later refiner iterations of a scale: x has not changed, d[:, 0:C] still holds the grid features
-#pragma unroll 4
-        for (int c = 0; c < C; ++c) {
-            const float* yp = yb + c * yplane;
-            float h = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) h = fmaf(__ldg(yp + tb.o[k]), tb.w[k], h);
-            __stcs(dp + (size_t)(C + c) * gg, h);
-        }
-    } else {
-#pragma unroll 4
-        for (int c = 0; c < C; ++c) {
+    // two separate loops: interleaving the lattice taps of x with the flow taps of y halves the achieved bandwidth
+    if (!keep_grid) {           // (later refiner iterations of a scale: x has not changed, d[:, 0:C] still holds the grid features)
+#pragma unroll 8
+        for (int c = c_lo; c < c_hi; ++c) {
             const float* xp = xb + c * xplane;
-            const float* yp = yb + c * yplane;
-            float a = 0.f, h = 0.f;
+            float a = 0.f;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                a = fmaf(__ldg(xp + ta.o[k]), ta.w[k], a);
-                h = fmaf(__ldg(yp + tb.o[k]), tb.w[k], h);
-            }
+            for (int k = 0; k < 4; ++k) a = fmaf(__ldg(xp + ta.o[k]), ta.w[k], a);
             dp[(size_t)c * gg] = a;          // read again by the correlation kernel: no streaming hint
-            __stcs(dp + (size_t)(C + c) * gg, h);
         }
+    }
+#pragma unroll 8
+    for (int c = c_lo; c < c_hi; ++c) {
+        const float* yp = yb + c * yplane;
+        float h = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h = fmaf(__ldg(yp + tb.o[k]), tb.w[k], h);
+        __stcs(dp + (size_t)(C + c) * gg, h);
     }
     const float vx = emb_scale * (fx - lxn), vy = emb_scale * (fy - lyn);
 #pragma unroll 4
-    for (int o = 0; o < dd; ++o)
+    for (int o = o_lo; o < o_hi; ++o)
         __stcs(dp + (size_t)(2 * C + o) * gg, fmaf(__ldg(w + 2 * o + 1), vy, fmaf(__ldg(w + 2 * o), vx, __ldg(bias + o))));
 }
 
@@ -100,9 +99,12 @@ extern "C" int gfb_refiner_assemble_f32(const float* x, const float* y, const fl
     GFB_CHECK_ARG(x && y && flow && d && (dd == 0 || (w && bias)));
     GFB_CHECK_ARG(B > 0 && C > 0 && Hs > 0 && Ws > 0 && G > 0 && dd >= 0 && Dtot >= 2 * C + dd);
     GFB_CHECK_ARG(y_pitch == 0 || y_pitch >= Ws);
-    GFB_CHECK_ARG((size_t)C * Hs * (y_pitch ? y_pitch : Ws) < (1ull << 31) && B <= 65535 && G <= 65535 * 4);
-    dim3 grid((G + 31) / 32, (G + 3) / 4, B), block(32, 4);
+    GFB_CHECK_ARG((size_t)C * Hs * (y_pitch ? y_pitch : Ws) < (1ull << 31) && B <= 65535 && G <= 23170);
+    // small lattices: split the channels over blockIdx.z so that every SM gets several blocks
+    int cpb = C;
+    while (cpb > 8 && cpb % 2 == 0 && (long long)((G * G + 255) / 256) * B * (C / cpb) < 148 * 8) cpb /= 2;
+    dim3 grid((G * G + 255) / 256, B, (C + cpb - 1) / cpb), block(256);
     refiner_assemble_kernel<<<grid, block, 0, gfb_cu(stream)>>>(x, y, flow, w, bias, d, C, Hs, Ws, y_pitch ? y_pitch : Ws, G, dd,
-                                                                  Dtot, emb_scale, keep_grid);
+                                                                  Dtot, emb_scale, keep_grid, cpb);
     GFB_LAUNCH_RESULT();
 }
