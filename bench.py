@@ -141,6 +141,34 @@ def cpu_reference_run(synth, args, steps, warmup, sample_pairs=1):
     return value, base, dt
 
 
+def gpu_reference_run(synth, args, dev, pairs=2, steps=3, warmup=1):
+    """the reference's OWN functions on the SAME B200 (torch CUDA kernels; fp16 kde at down = 1 and cv2 on the
+    host, exactly what the reference does on a GPU) -- a secondary baseline next to the CPU arm the task defines.  Bounded:
+    `pairs` pairs per step.  Returns a dict or None when the reference sources are not staged."""
+    import torch
+    from oracle import reference as R
+    from oracle.pipeline import cpu_hot_path
+    if not R.available():
+        return None
+    R.load_reference()
+    res, up, _ = synth.WORKLOADS[args.config]
+    batches = [synth.PairBatch(pairs, res=res, upsample_res=up, num_itr=NUM_ITR, seed=1234, device=dev, pair_offset=i) for i in range(2)]
+    for w in range(warmup):
+        cpu_hot_path(batches[w % 2], impl="reference")
+    torch.cuda.synchronize()
+    timings = {}
+    t0 = time.perf_counter()
+    for s_ in range(steps):
+        cpu_hot_path(batches[s_ % 2], timings=timings, impl="reference")
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": pairs * steps / dt, "unit": UNIT, "pairs_per_step": pairs, "steps": steps,
+            "what": "the reference's own local_correlation / corr_volume / pos_embed / sample (kde half=True, down=1) and the torch "
+                    "calls of ConvRefiner.forward :537-555 on this GPU (torch " + torch.__version__ + " CUDA kernels, fp32 features), "
+                    "cv2.findHomography on the host; wall clock with a device synchronise on both sides",
+            "seconds_by_stage_per_pair": {k: v / (pairs * steps) for k, v in timings.items()}}
+
+
 def run_reference(args):
     """--impl reference: rank 0 times the reference's CPU path (see cpu_reference_run); other ranks exit."""
     rank = int(os.environ.get("RANK", "0"))
@@ -301,9 +329,13 @@ def run_ours(args):
                     "algorithmic_bytes_per_step": lc_bytes, "launches_per_step": n_lc // max(args.steps, 1),
                     "share_of_step": lc_ms / total_ms if total_ms else None, "by_scale": by_scale}
         # CPU baseline on this box's host cores: bounded sample (1 pair x 2 steps) of the reference's own functions
-        cpu = None
+        cpu, gpu_ref = None, None
         if not args.no_cpu_baseline:
             _, cpu, _ = cpu_reference_run(synth, args, 2, 1)
+            try:
+                gpu_ref = gpu_reference_run(synth, args, dev)
+            except Exception as exc:                   # secondary figure: never fail the bench line over it
+                gpu_ref = {"unavailable": repr(exc)[:200]}
         line = {"metric": metric_name(args, synth), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": CONFIGS[args.config][1], "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(args, world, B, synth),
@@ -311,7 +343,7 @@ def run_ours(args):
                 "clocks": clocks, "gpu_launches": hp.kernel_launches(batch) * args.steps,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                         "overlap": "upload of step i+1 on a copy stream while step i computes (two device input sets)"},
-                "roofline": roofline, "cpu_baseline": cpu,
+                "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": gpu_ref,
                 "ace_px_mean": float(out["err"].mean()), "solved": int(out["status"].sum())}
         print(json.dumps(line))
     if world > 1:

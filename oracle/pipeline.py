@@ -6,6 +6,8 @@ TEST INFRASTRUCTURE / CPU BASELINE ONLY (tests, bench.py ``cpu_baseline`` and ``
 does; the two stretches of the reference that cannot be imported (the tail of ``GFNet.match``, model/network.py:358-384,
 which is inline in a method that needs the backbone, and estimation.py, which imports kornia) are the oracle ports.
 ``impl="port"`` uses the oracle ports throughout (same torch / cv2 operators in the same order).
+With ``impl="reference"`` the batch may live on a CUDA device: the same reference functions then run as the reference runs
+them on a GPU (torch CUDA kernels, fp16 kde at ``down=1`` -- model/network.py:405-408), cv2 on the host as in estimation.py.
 """
 import time
 
@@ -53,7 +55,7 @@ def cpu_hot_path(batch, num_samples=5000, seed=0, timings=None, impl="port", noi
                 if sc.get("x") is not None:          # refiner input assembly, the torch calls of ConvRefiner.forward :537-555
                     ta = time.perf_counter()
                     x_hat = F.grid_sample(sc["f1"], fl.permute(0, 2, 3, 1).contiguous(), align_corners=False, mode="bilinear")
-                    tt = torch.linspace(-1 + 1 / G, 1 - 1 / G, G)
+                    tt = torch.linspace(-1 + 1 / G, 1 - 1 / G, G, device=fl.device)
                     gy, gx = torch.meshgrid((tt, tt), indexing="ij")
                     coords = torch.stack((gx, gy))[None].expand(b, 2, G, G)
                     f0 = F.grid_sample(sc["x"], coords.permute(0, 2, 3, 1), align_corners=False, mode="bilinear")
@@ -86,10 +88,10 @@ def cpu_hot_path(batch, num_samples=5000, seed=0, timings=None, impl="port", noi
             m, c, _, _, _ = sample_port(warp[i], cert[i], num_samples, q1, q2, half=False, down=kde_down)
         tick("sample_kde", t0)
         t0 = time.perf_counter()
-        mn = m.numpy()
+        mn = m.detach().float().cpu().numpy()
         pa, pb = convert_coordinates(mn[:, :2], mn[:, 2:], res, res, res, res)                               # estimation.py:62-64
         H, _, _ = find_homography_cv2(pa, pb)                                                                # :66-77
-        errs.append(corner_error(H, batch.H_gt[i].numpy(), res, res))                                        # :79-92
+        errs.append(corner_error(H, batch.H_gt[i].cpu().numpy(), res, res))                                        # :79-92
         Hs.append(H)
         ms.append(mn)
         tick("homography", t0)

@@ -404,7 +404,14 @@ def test_sample_bit_exact_indices(gf, golden):
     # second draw: bit-exact given the same density (kde differs in the last bits between implementations)
     p = oracle.balanced_probability(rho[0].cpu().clone())
     assert torch.equal(idx2[0].cpu(), oracle.multinomial_from_noise(p, q2, num))
-    if torch.equal(idx2[0].cpu(), ridx2):                # and, when no near-tie flipped, the reference's own answer
+    # against the reference's own recorded answer: a near-tie in p/q can flip where the two densities differ in the last
+    # bits, so the number of differing draws is counted, printed and bounded (0 on the B200 runs so far)
+    ours, theirs = set(idx2[0].cpu().tolist()), set(ridx2.tolist())
+    diff = len(ours ^ theirs) // 2
+    print(f"balanced sampling, second draw: {diff} of {num} indices differ from the reference's recorded draw")
+    assert diff <= max(1, num // 200)
+    if diff == 0:
+        assert torch.equal(idx2[0].cpu(), ridx2)
         assert torch.equal(m[0].cpu(), torch.from_numpy(g["good_matches"]))
         assert torch.equal(c[0].cpu(), torch.from_numpy(g["good_certainty"]))
     assert torch.equal(m[0].cpu(), warp.reshape(-1, 4)[idx1[0].cpu()][idx2[0].cpu()])
