@@ -302,6 +302,9 @@ static int launch_pt(const LcParams& p, cudaStream_t st) {
 // tile: 8.8 staged pixels per point in the median instead of 16); (2) barriers: a producer warp (geometry of the next
 // tile, tile descriptor, TMA issue) and eight consumer warps meet only through full / empty mbarriers, there is no
 // CTA-wide barrier in the main loop.
+#ifndef ROT_MINB
+#define ROT_MINB 2
+#endif
 namespace rot {
 constexpr int R = 2, W = 6, KW = 5, KK = 25;
 constexpr int TX = 16, TY = 16, NT = TX * TY, NCW = NT / 32;     // tile, consumer warps
@@ -333,7 +336,7 @@ __device__ __forceinline__ void rot6(float (&v)[6], int n) {
 // channels.  Producer warp (one lane): waits for `gready` of a tile, picks the TMA box, publishes the descriptor
 // (`tfull`) and streams the channels through the ring (each stage = one channel of the f1 box + the 16 x 16 f0 tile).
 template <int C, int NBUF, int MBW, int MBH>
-__global__ void __launch_bounds__(rot::NT + 32, 2)
+__global__ void __launch_bounds__(rot::NT + 32, ROT_MINB)
 lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::Maps maps,
               const __grid_constant__ CUtensorMap tmap0) {
     using namespace rot;
