@@ -150,8 +150,8 @@ constexpr int ATOM_BYTES = TM * 128; // one K atom: 128 rows x 32 fp32
 // Load rows [n0, n0+128) x channels [0, KA*32) of src[C][N] (zero-padded), split hi/lo, store swizzled.
 template <int KA>
 __device__ __forceinline__ void load_split_tile(unsigned char* hi, unsigned char* lo, const float* __restrict__ src,
-                                                int C, int N, int n0, bool want_lo) {
-    const int r = threadIdx.x;  // one tile row per thread: coalesced across the CTA for every channel
+                                                int C, int N, int n0, bool want_lo, const int r) {
+    // one tile row per loader thread: coalesced across the 128 loaders for every channel
     const int n = n0 + r;
     const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
     // 32 loads in flight per thread before anything is converted: with one 128-thread CTA per SM the tile load is pure
@@ -181,35 +181,45 @@ __device__ __forceinline__ void load_split_tile(unsigned char* hi, unsigned char
     }
 }
 
+// Roles: warps 0-3 = softmax epilogue (thread = TMEM lane = source position), warps 4-7 = loaders (thread = tile row: NCHW
+// -> TF32 hi/lo, K-major, swizzled), warp 8 = MMA issuer.  They meet only through mbarriers, so the conversion of target tile
+// j+1 runs while tile j is in the tensor core and tile j-1 in the softmax (round 1 ran the three phases back to back in one
+// 4-warp CTA: tensor pipe 10 %).
+constexpr int GM_THREADS = 9 * 32;
+
 template <int KA>
-__global__ void __launch_bounds__(128, 1) gm_tc_kernel(const float* __restrict__ f0, const float* __restrict__ f1,
-                                                       float* __restrict__ flow, float* __restrict__ vol,
-                                                       int C, int N0, int N1, int H1, int W1, int precision) {
+__global__ void __launch_bounds__(GM_THREADS, 1) gm_tc_kernel(const float* __restrict__ f0, const float* __restrict__ f1,
+                                                              float* __restrict__ flow, float* __restrict__ vol,
+                                                              int C, int N0, int N1, int H1, int W1, int precision) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int TILE_BYTES = KA * ATOM_BYTES;
     unsigned char* a_hi = smem;
     unsigned char* a_lo = smem + TILE_BYTES;
     unsigned char* b_hi[2] = {smem + 2 * TILE_BYTES, smem + 4 * TILE_BYTES};
     unsigned char* b_lo[2] = {smem + 3 * TILE_BYTES, smem + 5 * TILE_BYTES};
-    __shared__ uint64_t mma_bar[2];
+    __shared__ uint64_t mma_bar[2];      // MMA into accumulator / from B buffer `buf` retired
+    __shared__ uint64_t b_full[2];       // B buffer written by the 128 loader threads
+    __shared__ uint64_t d_free[2];       // accumulator drained by the 4 epilogue warps
+    __shared__ uint64_t a_full;
     __shared__ uint32_t tmem_base_s;
     __shared__ float gxs[64], gys[64];  // not used when W1/H1 > 64 (falls back to gm_linspace)
 
     const int b = blockIdx.y, i0 = blockIdx.x * TM;
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool want_lo = precision == 0;
     const float* f0b = f0 + (size_t)b * C * N0;
     const float* f1b = f1 + (size_t)b * C * N1;
 
-    if (threadIdx.x == 0) { mbar_init(&mma_bar[0], 1); mbar_init(&mma_bar[1], 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 2; ++k) { mbar_init(&mma_bar[k], 1); mbar_init(&b_full[k], 128); mbar_init(&d_free[k], 4); }
+        mbar_init(&a_full, 128);
+        mbar_fence_init();
+    }
     if (warp == 0) tmem_alloc(&tmem_base_s, 256);
     if (threadIdx.x < 64) {
         gxs[threadIdx.x] = gm_linspace(W1, min((int)threadIdx.x, W1 - 1));
         gys[threadIdx.x] = gm_linspace(H1, min((int)threadIdx.x, H1 - 1));
     }
-    load_split_tile<KA>(a_hi, a_lo, f0b, C, N0, i0, want_lo);
-    load_split_tile<KA>(b_hi[0], b_lo[0], f1b, C, N1, 0, want_lo);
-    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -217,81 +227,132 @@ __global__ void __launch_bounds__(128, 1) gm_tc_kernel(const float* __restrict__
     constexpr uint32_t IDESC = idesc_tf32(TM, TM);
     const int ntiles = (N1 + TM - 1) / TM;
 
-    auto issue = [&](int buf) {   // one thread: D[buf] = A * B[buf]^T over K = KA*32 in steps of 8
-        const uint32_t d = tmem_base + (uint32_t)buf * TM;
-        uint32_t acc = 0;
-#pragma unroll
-        for (int ka = 0; ka < KA; ++ka) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t off = (uint32_t)ka * ATOM_BYTES + (uint32_t)ks * 32u;
-                const uint64_t ah = smem_desc_k128(smem_u32(a_hi) + off), bh = smem_desc_k128(smem_u32(b_hi[buf]) + off);
-                if (want_lo) {
-                    const uint64_t al = smem_desc_k128(smem_u32(a_lo) + off), bl = smem_desc_k128(smem_u32(b_lo[buf]) + off);
-                    mma_tf32(d, al, bh, IDESC, acc); acc = 1;
-                    mma_tf32(d, ah, bl, IDESC, acc);
-                }
-                mma_tf32(d, ah, bh, IDESC, acc); acc = 1;
-            }
-        }
-        mma_commit(&mma_bar[buf]);
-    };
-    if (threadIdx.x == 0) issue(0);
-
-    const int i = i0 + threadIdx.x;          // this thread's source position = TMEM lane
-    const float inv = 1.f / sqrtf((float)C), sc = 1.4426950408889634f * inv;
-    const bool small_grid = W1 <= 64 && H1 <= 64;
-    float m = -INFINITY, l = 0.f, sx = 0.f, sy = 0.f;
-    uint32_t phase[2] = {0, 0};
-    for (int jt = 0; jt < ntiles; ++jt) {
-        const int buf = jt & 1;
-        if (jt + 1 < ntiles) {
-            // B[buf^1] was last read by MMA(jt-1), whose completion every thread has observed;
-            // TMEM[buf^1] was drained by epilogue(jt-1) (fence_before_sync below + this barrier)
-            load_split_tile<KA>(b_hi[buf ^ 1], b_lo[buf ^ 1], f1b, C, N1, (jt + 1) * TM, want_lo);
+    if (warp >= 4 && warp < 8) {
+        // ================= loaders =================
+        const int r = threadIdx.x - 128;
+        load_split_tile<KA>(a_hi, a_lo, f0b, C, N0, i0, want_lo, r);
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&a_full);
+        for (int jt = 0; jt < ntiles; ++jt) {
+            const int buf = jt & 1;
+            if (jt >= 2) mbar_wait(&mma_bar[buf], ((jt >> 1) - 1) & 1);      // MMA(jt - 2) has read B[buf]
+            load_split_tile<KA>(b_hi[buf], b_lo[buf], f1b, C, N1, jt * TM, want_lo, r);
             fence_proxy_async();
-            fence_before_sync();
-            __syncthreads();
+            mbar_arrive(&b_full[buf]);
+        }
+    } else if (warp == 8) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            mbar_wait(&a_full, 0);
+            for (int jt = 0; jt < ntiles; ++jt) {
+                const int buf = jt & 1;
+                mbar_wait(&b_full[buf], (jt >> 1) & 1);
+                if (jt >= 2) mbar_wait(&d_free[buf], ((jt >> 1) - 1) & 1);   // epilogue(jt - 2) has drained TMEM[buf]
+                fence_after_sync();
+                const uint32_t d = tmem_base + (uint32_t)buf * TM;           // D[buf] = A * B[buf]^T over K = KA*32 in steps of 8
+                uint32_t acc = 0;
+#pragma unroll
+                for (int ka = 0; ka < KA; ++ka) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t off = (uint32_t)ka * ATOM_BYTES + (uint32_t)ks * 32u;
+                        const uint64_t ah = smem_desc_k128(smem_u32(a_hi) + off), bh = smem_desc_k128(smem_u32(b_hi[buf]) + off);
+                        if (want_lo) {
+                            const uint64_t al = smem_desc_k128(smem_u32(a_lo) + off), bl = smem_desc_k128(smem_u32(b_lo[buf]) + off);
+                            mma_tf32(d, al, bh, IDESC, acc); acc = 1;
+                            mma_tf32(d, ah, bl, IDESC, acc);
+                        }
+                        mma_tf32(d, ah, bh, IDESC, acc); acc = 1;
+                    }
+                }
+                mma_commit(&mma_bar[buf]);
+            }
+        }
+    } else {
+        // ================= epilogue: online softmax x grid expectation =================
+        const int i = i0 + threadIdx.x;          // this thread's source position = TMEM lane
+        const float inv = 1.f / sqrtf((float)C), sc = 1.4426950408889634f * inv;
+        const bool small_grid = W1 <= 64 && H1 <= 64;
+        // Fast path (W1 >= 32, whole chunks): the grid is linear in the column / row index, so a chunk of 32 target positions
+        // only needs P = sum p, T = sum p * e (e = position inside the chunk, an immediate) and Q = sum of the p past the one
+        // row wrap a chunk can contain:  sum p * jx = jx0 P + T - W1 Q,  sum p * jy = jy0 P + Q.  Six instructions per
+        // element instead of ~38 (the per-element row / column bookkeeping made the softmax warps the bottleneck).
+        const bool fast = W1 >= 32 && !vol;
+        float m = -INFINITY, l = 0.f, sx = 0.f, sy = 0.f;      // fast path: sx / sy accumulate p * jx / p * jy
+        for (int jt = 0; jt < ntiles; ++jt) {
+            const int buf = jt & 1;
+            mbar_wait(&mma_bar[buf], (jt >> 1) & 1);
             fence_after_sync();
-            if (threadIdx.x == 0) issue(buf ^ 1);
-        }
-        mbar_wait(&mma_bar[buf], phase[buf]);
-        phase[buf] ^= 1;
-        fence_after_sync();
-        const int j0 = jt * TM;
+            const int j0 = jt * TM;
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * TM + ch * 32), r);
-            tmem_ld_wait();
-            const int jb = j0 + ch * 32;
-            float cmax = -INFINITY;
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * TM + ch * 32), r);
+                tmem_ld_wait();
+                if (ch == 3) {                   // the accumulator is in registers: hand it back before the arithmetic
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d_free[buf]);
+                }
+                const int jb = j0 + ch * 32;
+                if (jb >= N1) continue;
+                int jy = jb / W1, jx = jb - jy * W1;
+                if (fast && jb + 32 <= N1) {
+                    float dmax = __uint_as_float(r[0]);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float d = __uint_as_float(r[e]);
-                if (vol && i < N0 && jb + e < N1) vol[((size_t)b * N1 + jb + e) * N0 + i] = d * inv;
-                cmax = fmaxf(cmax, (jb + e < N1) ? d * sc : -INFINITY);
-            }
-            if (cmax > m) { const float rs = ex2f(m - cmax); l *= rs; sx *= rs; sy *= rs; m = cmax; }
-            int jy = jb / W1, jx = jb - jy * W1;
+                    for (int e = 1; e < 32; ++e) dmax = fmaxf(dmax, __uint_as_float(r[e]));
+                    const float cmax = dmax * sc;
+                    if (cmax > m) { const float rs = ex2f(m - cmax); l *= rs; sx *= rs; sy *= rs; m = cmax; }
+                    const float nm = -m;
+                    const int ewrap = W1 - jx;                      // elements e >= ewrap sit on the next grid row
+                    float P = 0.f, T = 0.f, Q = 0.f;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const float s = (jb + e < N1) ? __uint_as_float(r[e]) * sc : -INFINITY;
-                const float pj = ex2f(s - m);
-                const float gx = small_grid ? gxs[jx] : gm_linspace(W1, jx);
-                const float gy = small_grid ? gys[min(jy, 63)] : gm_linspace(H1, jy);
-                l += pj;
-                sx = fmaf(pj, gx, sx);
-                sy = fmaf(pj, gy, sy);
-                if (++jx == W1) { jx = 0; ++jy; }
+                    for (int e = 0; e < 32; ++e) {
+                        const float pj = ex2f(fmaf(__uint_as_float(r[e]), sc, nm));
+                        P += pj;
+                        T = fmaf(pj, (float)e, T);
+                        if (e >= ewrap) Q += pj;
+                    }
+                    l += P;
+                    sx += fmaf((float)jx, P, T) - (float)W1 * Q;
+                    sy += fmaf((float)jy, P, Q);
+                    continue;
+                }
+                float cmax = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float d = __uint_as_float(r[e]);
+                    if (vol && i < N0 && jb + e < N1) vol[((size_t)b * N1 + jb + e) * N0 + i] = d * inv;
+                    cmax = fmaxf(cmax, (jb + e < N1) ? d * sc : -INFINITY);
+                }
+                if (cmax > m) { const float rs = ex2f(m - cmax); l *= rs; sx *= rs; sy *= rs; m = cmax; }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float s = (jb + e < N1) ? __uint_as_float(r[e]) * sc : -INFINITY;
+                    const float pj = ex2f(s - m);
+                    // fast mode accumulates indices (the partial last chunk of a fast run lands here)
+                    const float gx = fast ? (float)jx : small_grid ? gxs[jx] : gm_linspace(W1, jx);
+                    const float gy = fast ? (float)jy : small_grid ? gys[min(jy, 63)] : gm_linspace(H1, jy);
+                    l += pj;
+                    sx = fmaf(pj, gx, sx);
+                    sy = fmaf(pj, gy, sy);
+                    if (++jx == W1) { jx = 0; ++jy; }
+                }
             }
         }
-        fence_before_sync();  // TMEM[buf] reads are done before the barrier that precedes its next MMA
+        if (i < N0) {
+            float fx = sx / l, fy = sy / l;
+            if (fast) {          // expectation of the index -> expectation of torch.linspace(-1 + 1/n, 1 - 1/n, n)
+                const float x0 = (float)(-1.0 + 1.0 / (double)W1), x1 = (float)(1.0 - 1.0 / (double)W1);
+                const float y0 = (float)(-1.0 + 1.0 / (double)H1), y1 = (float)(1.0 - 1.0 / (double)H1);
+                fx = fmaf((x1 - x0) / (float)(W1 - 1), fx, x0);
+                fy = H1 > 1 ? fmaf((y1 - y0) / (float)(H1 - 1), fy, y0) : y0;
+            }
+            flow[((size_t)b * 2 + 0) * N0 + i] = fx;
+            flow[((size_t)b * 2 + 1) * N0 + i] = fy;
+        }
     }
-    if (i < N0) {
-        flow[((size_t)b * 2 + 0) * N0 + i] = sx / l;
-        flow[((size_t)b * 2 + 1) * N0 + i] = sy / l;
-    }
+    fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
@@ -326,12 +387,12 @@ extern "C" int gfb_global_match_f32(const float* f0, const float* f1, float* flo
             const int smem = 6 * 1 * tc::ATOM_BYTES;
             e = cudaFuncSetAttribute(tc::gm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int)e;
-            tc::gm_tc_kernel<1><<<grid, 128, smem, st>>>(f0, f1, flow_out, vol_out, C, N0, N1, H1, W1, precision);
+            tc::gm_tc_kernel<1><<<grid, tc::GM_THREADS, smem, st>>>(f0, f1, flow_out, vol_out, C, N0, N1, H1, W1, precision);
         } else {
             const int smem = 6 * 2 * tc::ATOM_BYTES;
             e = cudaFuncSetAttribute(tc::gm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int)e;
-            tc::gm_tc_kernel<2><<<grid, 128, smem, st>>>(f0, f1, flow_out, vol_out, C, N0, N1, H1, W1, precision);
+            tc::gm_tc_kernel<2><<<grid, tc::GM_THREADS, smem, st>>>(f0, f1, flow_out, vol_out, C, N0, N1, H1, W1, precision);
         }
         GFB_LAUNCH_RESULT();
     }
