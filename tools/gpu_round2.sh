@@ -2,7 +2,7 @@
 # Round-2 measurement artefacts (run on the GPU box; results land in gpurun_out/, copied to profiles/ by hand).
 set -x
 mkdir -p gpurun_out
-for tool in ; do
+for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize.py > gpurun_out/r2_sanitizer_$tool.log 2>&1
   tail -4 gpurun_out/r2_sanitizer_$tool.log
 done
