@@ -32,9 +32,6 @@ _MMA_SHAPES = {(1, 16), (2, 16), (2, 32), (3, 32), (4, 32)} | {(r, 64) for r in 
 # local_correlation_prepare: one launch instead of pre-pass + plan + main (measured, op batch 64: 0.133 vs 0.167 ms at
 # (32,112,64,4), 0.193 vs 0.435 ms at (32,140,80,4); the 64-channel shapes stay on the tcgen05 kernel)
 _MMA_AUTO = {(2, 32), (3, 32), (4, 32)}
-import os as _os
-if _os.environ.get("GFB_MMA_AUTO"):  # tuning knob: "4x32,6x64" (radius x channels)
-    _MMA_AUTO = {tuple(int(v) for v in t.split("x")) for t in _os.environ["GFB_MMA_AUTO"].split(",")}
 
 
 def _tc2_slice_channels(r, c):
