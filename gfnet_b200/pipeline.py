@@ -39,6 +39,12 @@ class HotPath:
         return n
 
     def run(self, batch, generator=None, noise=None):
+        out = self.run_front(batch)
+        out.update(self.run_back(batch, generator=generator, noise=noise))
+        return out
+
+    def run_front(self, batch):
+        """Dense part: coarse global match + the refiner input of every scale / iteration / pass (kernels that fill the GPU)."""
         out = {}
         out["coarse_flow"] = ops.coarse_match(batch.coarse_f0, batch.coarse_f1, precision=self.precision)
         for pi, scales in enumerate(batch.passes):
@@ -64,6 +70,12 @@ class HotPath:
                         e1.record()
                         self.timing.append((f"pass{pi + 1}_scale{sc['scale']}", e0, e1))
         out["last_corr"] = buf
+        return out
+
+    def run_back(self, batch, generator=None, noise=None):
+        """Sparse tail: match post-process, balanced sampling (top-k, kde), homography, corner error -- per-pair kernels that
+        leave most SMs idle (32 CTAs), so a throughput loop may run it on a second stream under the next batch's dense part."""
+        out = {}
         warp, cert = matcher.match_postprocess(batch.final_flow, batch.cert_logits, symmetric=True)
         m, c = matcher.sample_batched(warp, cert, self.num_samples, generator=generator, noise=noise)
         res = batch.res
