@@ -393,13 +393,15 @@ lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::M
                 const int b = t / tiles_y;
                 const CUtensorMap* tm = &maps.m[bwi][bhi];
                 const uint32_t bytes = (uint32_t)((box_w(bwi) * box_h(bhi) + NT) * sizeof(float));
-                for (int c = 0; c < C; ++c, ++q) {
+                for (int c = 0; c < C; c += 2, q += 2) {         // one full / empty pair per two channels (slots s, s + 1)
                     const uint32_t s = q % NBUF;
                     mbar_wait(&empty[s], ((q / NBUF) & 1) ^ 1);
                     if (p.debug & 2) { mbar_arrive(&full[s]); continue; }
-                    mbar_expect_tx(&full[s], bytes);
+                    mbar_expect_tx(&full[s], 2 * bytes);
                     tma_load_3d(ring + s * SLOT, tm, &full[s], X0, Y0, b * C + c);
                     tma_load_3d(ring + s * SLOT + BOXMAX, &tmap0, &full[s], tx * TX, ty * TY, b * p.f0_ctot + c);
+                    tma_load_3d(ring + (s + 1) * SLOT, tm, &full[s], X0, Y0, b * C + c + 1);
+                    tma_load_3d(ring + (s + 1) * SLOT + BOXMAX, &tmap0, &full[s], tx * TX, ty * TY, b * p.f0_ctot + c + 1);
                 }
             }
         }
@@ -499,7 +501,6 @@ lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::M
                 const uint32_t s = q % NBUF;
                 const uint32_t par = (q / NBUF) & 1;
                 mbar_wait(&full[s], par);
-                mbar_wait(&full[s + 1], par);
                 if (fit && !(p.debug & 1)) {
                     const unsigned char* sb = ring_b + s * (SLOT * 4);
                     const float fa = *reinterpret_cast<const float*>(sb + (BOXMAX + tid) * 4);
@@ -521,7 +522,7 @@ lc_rot_kernel(const LcParams p, const int ntiles, const __grid_constant__ rot::M
                     }
                 }
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&empty[s]); mbar_arrive(&empty[s + 1]); }
+                if (lane == 0) mbar_arrive(&empty[s]);
             }
         }
 
