@@ -91,6 +91,32 @@ def test_refiner_input_iterations_reuse_the_prepass(ref):
     assert not torch.equal(first, fresh)
 
 
+@pytest.mark.parametrize("c,hs,ws,G,scale", [(32, 40, 56, 24, 4), (16, 50, 36, 28, 2), (64, 24, 40, 20, 8)])
+def test_refiner_input_non_square_maps(ref, c, hs, ws, G, scale):
+    """hs != ws, ws % 4 != 0, G not a multiple of 8: the general shapes of the reference's signature (b, c, hs, ws)."""
+    import gfnet_b200 as gf
+    from gfnet_b200 import synth
+    torch.manual_seed(3)
+    cr = R.make_conv_refiner(ref, scale).cuda().eval()
+    r = cr.local_corr_radius
+    gen = torch.Generator(device="cuda").manual_seed(c + hs)
+    x = torch.randn((2, c, hs, ws), generator=gen, device="cuda")
+    y = torch.randn((2, c, hs, ws), generator=gen, device="cuda")
+    flow = (synth.lattice(G, "cuda")[None] * 0.9 + 0.05 * torch.randn((2, 2, G, G), generator=gen, device="cuda")).contiguous()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.inference_mode():
+            want = _reference_d(ref, cr, G, x, y, flow, 1.0)
+            got = gf.refiner_input(G, x, y, flow, cr.disp_emb.weight, cr.disp_emb.bias, r)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    k = (2 * r + 1) ** 2
+    scale_ = float(want[:, -k:].abs().max())
+    assert float((got[:, :-k] - want[:, :-k]).abs().max()) <= 2e-6 * float(want[:, :-k].abs().max())
+    assert float((got[:, -k:] - want[:, -k:]).abs().max()) <= 1.4e-4 * scale_
+
+
 def test_refiner_input_rejects_cpu_tensors():
     import gfnet_b200 as gf
     x = torch.zeros((1, 16, 8, 8))
