@@ -127,7 +127,7 @@ def test_local_correlation_reference_fixture_real_shapes(gf, golden):
         _close(out[:, :, ::st, ::st], ref, atol_rel=1e-5 if hs <= 112 else 4e-5)
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 32, 32, 7), (64, 16, 224, 128, 2)])
+@pytest.mark.parametrize("shape", [(64, 64, 32, 32, 7), (64, 32, 112, 64, 4), (64, 16, 224, 128, 2)])
 def test_local_correlation_full_batch_vs_oracle_port(gf, shape):
     """BASELINE config 2's op batch (64) against the oracle port itself (not only against our own gather kernel)."""
     from gfnet_b200 import synth
