@@ -18,6 +18,9 @@ EXPORTS = [
     "gfb_debug_local_corr_v2_counters", "gfb_debug_local_corr_tc2_f32", "gfb_debug_local_corr_pt_f32",
     "gfb_global_match_f32", "gfb_pos_embed_f32", "gfb_kde_f32", "gfb_kde_sym_workspace_bytes", "gfb_kde_sym_f32", "gfb_match_postprocess_f32",
     "gfb_sample_keys_f32", "gfb_balance_keys_f32", "gfb_gather_matches_f32", "gfb_topk_workspace_bytes",
+    "gfb_refiner_pack_f16", "gfb_refiner_dw5_f16", "gfb_refiner_pw_f16", "gfb_refiner_out_f32", "gfb_refiner_blocks_weight_bytes",
+    "gfb_refiner_blocks_chunk", "gfb_refiner_blocks_workspace_bytes", "gfb_refiner_blocks_f16", "gfb_flow_update_f32",
+    "gfb_upsample_bilinear_f32",
     "gfb_topk_desc_f32", "gfb_homography_workspace_bytes", "gfb_homography_f32", "gfb_homography_cv_f32", "gfb_corner_error_f64",
 ]
 
@@ -55,6 +58,18 @@ def _load():
     lib.gfb_local_corr_mma_f32.argtypes = [vp, vp, vp, vp] + [i32] * 13 + [vp]
     lib.gfb_refiner_assemble_f32.argtypes = [vp] * 6 + [i32] * 8 + [f32, i32, vp]
     lib.gfb_local_corr_cat_f32.argtypes = [vp, i32, vp, vp] + [i32] * 9 + [vp, sz, vp]
+    lib.gfb_refiner_pack_f16.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.gfb_refiner_dw5_f16.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.gfb_refiner_pw_f16.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
+    lib.gfb_refiner_out_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.gfb_refiner_blocks_weight_bytes.restype = sz
+    lib.gfb_refiner_blocks_weight_bytes.argtypes = [i32, i32, i32]
+    lib.gfb_refiner_blocks_chunk.argtypes = [i32, i32, i32]
+    lib.gfb_refiner_blocks_workspace_bytes.restype = sz
+    lib.gfb_refiner_blocks_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.gfb_refiner_blocks_f16.argtypes = [vp, vp, vp] + [i32] * 5 + [vp, sz, i32, i32, vp]
+    lib.gfb_flow_update_f32.argtypes = [vp, vp, vp, vp] + [i32] * 6 + [vp]
+    lib.gfb_upsample_bilinear_f32.argtypes = [vp, vp] + [i32] * 5 + [vp]
     lib.gfb_debug_local_corr_mma_counters.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), i32]
     lib.gfb_debug_local_corr_v2_counters.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), i32]
     lib.gfb_pad_rows_f32.argtypes = [vp, vp, i64, i32, i32, vp]
@@ -80,7 +95,8 @@ def _load():
     for name in EXPORTS:   # getattr raises AttributeError if the library lacks a declared symbol
         if name not in ("gfb_strerror", "gfb_topk_workspace_bytes", "gfb_homography_workspace_bytes",
                         "gfb_local_corr_tc2_workspace_bytes",
-                        "gfb_kde_sym_workspace_bytes"):
+                        "gfb_kde_sym_workspace_bytes", "gfb_refiner_blocks_weight_bytes",
+                        "gfb_refiner_blocks_workspace_bytes"):
             getattr(lib, name).restype = i32
     if lib.gfb_abi_version() != 2:
         raise ImportError("libgfnet_b200.so ABI version mismatch; rebuild with `make -C gfnet_b200/csrc`")

@@ -1,0 +1,565 @@
+// Refiner convolution blocks (reference: ConvRefiner.create_block / forward tail, model/network.py:505-531,
+// 557-563) and the flow update + between-scale upsampling of the decoder loop (model/network.py:262-285).
+//
+//   block(h) = conv2_1x1( relu( bn( dwconv5x5(h) ) ) )            9 blocks per refiner (block1 + 8 hidden), in_dim = hidden_dim
+//   delta    = out_conv_1x1( blocks(d).float() )                  hidden -> 3 (dx, dy, d_certainty), fp32
+//
+// The reference runs the blocks under fp16 autocast (amp=True at every call site, model/network.py:90).  Here activations are
+// stored as fp16 NHWC ([B, G*G, Cp], Cp = C rounded up to 16, pad channels zero) and every sum is accumulated in fp32:
+//   rb_pack_kernel   d [B,C,G,G] fp32 NCHW -> fp16 NHWC (the refiner input written by the assemble + correlation kernels)
+//   rb_dw_kernel     depth-wise 5x5 + batch norm (eval, folded into the taps + a shift) + ReLU; lane = channel pair, a warp
+//                    walks a 4-pixel-wide strip downwards with the 5 pending output rows in registers (packed f32x2 FMAs)
+//   rb_pw_kernel     the 1x1 convolution as a GEMM on tcgen05: A = 128 pixels x K (TMA, 128B swizzle), B = W2 rows (TMA),
+//                    fp32 accumulator in TMEM, epilogue adds the bias and writes fp16 NHWC; persistent over pixel tiles
+//   rb_out_kernel    out_conv (hidden -> 3) in fp32, NCHW output
+// gfb_refiner_blocks_f16 runs the chain for a batch chunk at a time so that the two ping-pong activation buffers of a chunk
+// stay in the 126 MB L2 across all nine blocks: HBM sees the refiner input once and the three output planes once.
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+namespace gfb {
+namespace rb {
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long h2_to_f2(uint32_t h) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    return pack2(f.x, f.y);
+}
+__device__ __forceinline__ uint32_t f2_to_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC fp16, 64 channels x 32 pixels per block through a shared-memory transpose
+__global__ void __launch_bounds__(256) rb_pack_kernel(const float* __restrict__ d, __half* __restrict__ out, int C, int Cp, int P) {
+    __shared__ float t[64][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 64; i += 8) {
+        const int c = c0 + i, p = p0 + tx;
+        t[i][tx] = (c < C && p < P) ? __ldcs(d + ((size_t)b * C + c) * P + p) : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int p = p0 + i, c = c0 + 2 * tx;
+        if (p < P && c < Cp)
+            *reinterpret_cast<uint32_t*>(out + ((size_t)b * P + p) * Cp + c) = f2_to_h2(t[2 * tx][i], t[2 * tx + 1][i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// depth-wise 5x5 (zero padding 2) + folded batch norm + ReLU on NHWC fp16.  wf [25][Cp] fp32 = tap * bn_scale, shift [Cp] =
+// (conv_bias - running_mean) * bn_scale + bn_bias.  A warp = 64 channels (lane = channel pair) x a strip of 4 x DW_TH outputs;
+// input row j of the strip feeds the five output rows j-4..j, whose accumulators live in a register ring (static slots: the
+// row loop is unrolled by five).
+constexpr int DW_TH = 16;      // output rows per strip ((DW_TH + 4) % 5 == 0)
+constexpr int DW_WARPS = 4;    // neighbouring strips of one channel chunk: their x halos meet in L1
+
+__global__ void __launch_bounds__(DW_WARPS * 32) rb_dw_kernel(const __half* __restrict__ in, const float* __restrict__ wf,
+                                                              const float* __restrict__ shift, __half* __restrict__ out,
+                                                              int G, int Cp, int nchunk) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x % nchunk, xs = blockIdx.x / nchunk;
+    const int c = (chunk * 32 + lane) * 2;
+    const int x0 = (xs * DW_WARPS + warp) * 4, y0 = blockIdx.y * DW_TH, b = blockIdx.z;
+    if (x0 >= G) return;
+    const bool cok = c < Cp;
+    unsigned long long w[25];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) w[t] = cok ? pack2(__ldg(wf + t * Cp + c), __ldg(wf + t * Cp + c + 1)) : 0ull;
+    const float sh0 = cok ? __ldg(shift + c) : 0.f, sh1 = cok ? __ldg(shift + c + 1) : 0.f;
+    unsigned long long acc[5][4];
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[s][p] = 0ull;
+    const __half* inb = in + (size_t)b * G * G * Cp + c;
+    __half* outb = out + (size_t)b * G * G * Cp + c;
+    bool xok[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xok[i] = cok && x0 - 2 + i >= 0 && x0 - 2 + i < G;
+
+#pragma unroll 1
+    for (int base = 0; base < DW_TH + 4; base += 5) {
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const int j = base + s, iy = y0 - 2 + j;
+            unsigned long long v[8];
+            const bool yok = iy >= 0 && iy < G;
+            const __half* row = inb + ((size_t)iy * G + (x0 - 2)) * Cp;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t h = 0u;
+                if (yok && xok[i]) h = __ldg(reinterpret_cast<const uint32_t*>(row + (size_t)i * Cp));
+                v[i] = h2_to_f2(h);
+            }
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky) {
+                const int slot = (s - ky + 5) % 5;       // output row j - ky
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) acc[slot][p] = fma2(w[ky * 5 + kx], v[p + kx], acc[slot][p]);
+            }
+            // output row o = j - 4 is complete (its last tap row ky = 4 was this input row): slot (s + 1) % 5
+            const int o = j - 4, oy = y0 + o, slot = (s + 1) % 5;
+            if (o >= 0 && oy < G && cok) {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float2 a = unpack2(acc[slot][p]);
+                    if (x0 + p < G)
+                        *reinterpret_cast<uint32_t*>(outb + ((size_t)oy * G + x0 + p) * Cp) =
+                            f2_to_h2(fmaxf(a.x + sh0, 0.f), fmaxf(a.y + sh1, 0.f));
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[slot][p] = 0ull;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 1x1 convolution = GEMM  out[p, n] = fp16( sum_k act[p, k] * w2[n, k] + bias[n] ),  p < P, n, k < Cp.
+// any-shape CUDA-core version (cross-check of the tcgen05 kernel; algo = 1)
+__global__ void __launch_bounds__(128) rb_pw_simt_kernel(const __half* __restrict__ act, const __half* __restrict__ w2,
+                                                         const float* __restrict__ bias, __half* __restrict__ out, size_t P, int Cp) {
+    const size_t p = blockIdx.x;
+    for (int n = threadIdx.x; n < Cp; n += 128) {
+        float a = 0.f;
+        for (int k = 0; k < Cp; ++k) a = fmaf(__half2float(act[p * Cp + k]), __half2float(w2[(size_t)n * Cp + k]), a);
+        out[p * Cp + n] = __float2half_rn(a + bias[n]);
+    }
+}
+
+// tcgen05 version -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// shared-memory matrix descriptor: K-major, 128B swizzle, 8-row groups 1024 B apart (sm_100 format)
+__device__ __forceinline__ uint64_t smem_desc_k128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N runtime
+__device__ __forceinline__ uint32_t idesc_f16(int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+struct PwParams {
+    const float* bias;
+    __half* out;
+    long long P;       // pixels (rows of act / out)
+    int Cp;            // padded channels: K extent, N extent, row pitch of act / w2 / out in halves
+    int NT;            // N tile (multiple of 16, <= 256); nsplit tiles cover Cp
+    int nsplit;
+    int KA;            // K atoms of 64 halves (128 B)
+    int klast;         // K steps of 16 in the last atom
+    int nstage;
+    int nwork;         // pixel tiles * nsplit
+};
+constexpr int PW_THREADS = 6 * 32;   // warp 0: TMA, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int PW_MAXSTAGE = 6;
+constexpr int PW_TMEM = 256;
+
+__global__ void __launch_bounds__(PW_THREADS, 2) rb_pw_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB, const PwParams g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full[PW_MAXSTAGE], empty[PW_MAXSTAGE], d_full[2], d_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)g.NT * 128, stage_bytes = a_bytes + b_bytes;
+    const int nacc = g.NT <= 128 ? 2 : 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], 4); }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, PW_TMEM);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int wk = blockIdx.x; wk < g.nwork; wk += gridDim.x) {
+                const int half = wk % g.nsplit, mt = wk / g.nsplit;
+                for (int ka = 0; ka < g.KA; ++ka, ++it) {
+                    const uint32_t s = it % g.nstage;
+                    mbar_wait(&empty[s], ((it / g.nstage) & 1) ^ 1);
+                    unsigned char* st = smem + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full[s], stage_bytes);
+                    tma_load_2d(st, &tmA, &full[s], ka * 32, mt * 128);
+                    tma_load_2d(st + a_bytes, &tmB, &full[s], ka * 32, half * g.NT);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = idesc_f16(g.NT);
+            uint32_t it = 0, t = 0;
+            for (int wk = blockIdx.x; wk < g.nwork; wk += gridDim.x, ++t) {
+                const uint32_t a = t % nacc;
+                mbar_wait(&d_empty[a], ((t / nacc) & 1) ^ 1);
+                fence_after_sync();
+                const uint32_t dt = tmem_base + a * 128u;
+                uint32_t accum = 0;
+                for (int ka = 0; ka < g.KA; ++ka, ++it) {
+                    const uint32_t s = it % g.nstage;
+                    mbar_wait(&full[s], (it / g.nstage) & 1);
+                    fence_after_sync();
+                    const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + a_bytes;
+                    const int nk = ka + 1 == g.KA ? g.klast : 4;
+                    for (int ks = 0; ks < nk; ++ks) {
+                        mma_f16(dt, smem_desc_k128(a_addr + ks * 32), smem_desc_k128(b_addr + ks * 32), idesc, accum);
+                        accum = 1;
+                    }
+                    mma_commit(&empty[s]);
+                }
+                mma_commit(&d_full[a]);
+            }
+        }
+    } else {
+        const int q = warp & 3;                        // TMEM lane quarter this warp may read
+        uint32_t t = 0;
+        for (int wk = blockIdx.x; wk < g.nwork; wk += gridDim.x, ++t) {
+            const int half = wk % g.nsplit, mt = wk / g.nsplit;
+            const uint32_t a = t % nacc;
+            mbar_wait(&d_full[a], (t / nacc) & 1);
+            fence_after_sync();
+            const long long p = (long long)mt * 128 + q * 32 + lane;
+            __half* orow = g.out + (size_t)p * g.Cp;
+            const int nchunks = (g.NT + 31) / 32;
+            for (int ch = 0; ch < nchunks; ++ch) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 128u + (uint32_t)ch * 32u, r);
+                tmem_ld_wait();
+                const int n0 = half * g.NT + ch * 32;
+#pragma unroll
+                for (int v8 = 0; v8 < 4; ++v8) {
+                    const int n = n0 + v8 * 8;
+                    if (ch * 32 + v8 * 8 < g.NT && n < g.Cp && p < g.P) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
+                        uint4 o;
+                        o.x = f2_to_h2(__uint_as_float(r[v8 * 8 + 0]) + b0.x, __uint_as_float(r[v8 * 8 + 1]) + b0.y);
+                        o.y = f2_to_h2(__uint_as_float(r[v8 * 8 + 2]) + b0.z, __uint_as_float(r[v8 * 8 + 3]) + b0.w);
+                        o.z = f2_to_h2(__uint_as_float(r[v8 * 8 + 4]) + b1.x, __uint_as_float(r[v8 * 8 + 5]) + b1.y);
+                        o.w = f2_to_h2(__uint_as_float(r[v8 * 8 + 6]) + b1.z, __uint_as_float(r[v8 * 8 + 7]) + b1.w);
+                        *reinterpret_cast<uint4*>(orow + n) = o;
+                    }
+                }
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[a]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, PW_TMEM);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// out_conv: fp32 1x1 convolution hidden -> OC (<= 4) on the fp16 activations, NCHW fp32 output.  L lanes per pixel.
+template <int L>
+__global__ void __launch_bounds__(256) rb_out_kernel(const __half* __restrict__ act, const float* __restrict__ w /*[OC][Cp]*/,
+                                                     const float* __restrict__ bias, float* __restrict__ out /*[B,OC,P]*/,
+                                                     int B, int P, int Cp, int OC) {
+    const int lane = threadIdx.x & 31, sub = lane % L;
+    const long long pix = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * (32 / L) + lane / L;
+    const long long total = (long long)B * P;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (pix < total) {
+        const __half* row = act + (size_t)pix * Cp;
+        for (int c = 2 * sub; c < Cp; c += 2 * L) {
+            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(row + c));
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (o < OC) acc[o] = fmaf(v.y, __ldg(w + o * Cp + c + 1), fmaf(v.x, __ldg(w + o * Cp + c), acc[o]));
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int m = L / 2; m > 0; m >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
+    if (pix < total && sub == 0) {
+        const long long b = pix / P, p = pix - b * P;
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (o < OC) out[((size_t)b * OC + o) * P + p] = acc[o] + __ldg(bias + o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// decoder-loop glue (model/network.py:262-285)
+// displacement = int(scale) * (delta / (4 W0), delta / (4 H0)) as torch evaluates it on CUDA (division by a Python scalar =
+// multiplication by its fp32 reciprocal); eval-mode zeroing of |disp - pre| / |pre| < 1e-6; flow += disp; certainty += delta_c
+__global__ void __launch_bounds__(256) flow_update_kernel(const float* __restrict__ delta /*[B,3,P]*/, float* __restrict__ flow,
+                                                          float* __restrict__ cert, float* __restrict__ pre, int B, int P,
+                                                          float scale, float inv4w, float inv4h, int zero_rule) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)B * P) return;
+    const long long b = i / P, p = i - b * P;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const float dl = delta[((size_t)b * 3 + ch) * P + p];
+        float disp = __fmul_rn(scale, __fmul_rn(dl, ch == 0 ? inv4w : inv4h));
+        const size_t o = ((size_t)b * 2 + ch) * P + p;
+        const float dp = pre[o];
+        if (zero_rule && __fdiv_rn(fabsf(__fsub_rn(disp, dp)), fabsf(dp)) < 1e-6f) disp = 0.f;
+        flow[o] = __fadd_rn(flow[o], disp);
+        pre[o] = disp;
+    }
+    cert[(size_t)b * P + p] = __fadd_rn(cert[(size_t)b * P + p], delta[((size_t)b * 3 + 2) * P + p]);
+}
+
+// F.interpolate(mode="bilinear", align_corners=False, size=(Ho, Wo)) as ATen's upsample_bilinear2d evaluates it
+__global__ void __launch_bounds__(256) upsample_bilinear_kernel(const float* __restrict__ in, float* __restrict__ out, int planes,
+                                                                int Hi, int Wi, int Ho, int Wo, float rh, float rw) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)planes * Ho * Wo) return;
+    const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+    const long long pl = i / ((long long)Wo * Ho);
+    const float sy = fmaxf(__fmaf_rn(rh, (float)oy + 0.5f, -0.5f), 0.f), sx = fmaxf(__fmaf_rn(rw, (float)ox + 0.5f, -0.5f), 0.f);
+    const int y1 = (int)sy, x1 = (int)sx;
+    const int yp = y1 < Hi - 1 ? 1 : 0, xp = x1 < Wi - 1 ? 1 : 0;
+    const float ly = sy - (float)y1, lx = sx - (float)x1, hy = 1.f - ly, hx = 1.f - lx;
+    const float* s = in + (size_t)pl * Hi * Wi;
+    const float v00 = s[(size_t)y1 * Wi + x1], v01 = s[(size_t)y1 * Wi + x1 + xp];
+    const float v10 = s[(size_t)(y1 + yp) * Wi + x1], v11 = s[(size_t)(y1 + yp) * Wi + x1 + xp];
+    out[i] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static inline int pad16(int c) { return (c + 15) / 16 * 16; }
+
+static int launch_pack(const float* d, __half* out, int B, int C, int Cp, int P, cudaStream_t st) {
+    dim3 grid((P + 31) / 32, (Cp + 63) / 64, B);
+    rb_pack_kernel<<<grid, 256, 0, st>>>(d, out, C, Cp, P);
+    return (int)cudaGetLastError();
+}
+static int launch_dw(const __half* in, const float* wf, const float* shift, __half* out, int B, int G, int Cp, cudaStream_t st) {
+    const int nchunk = (Cp + 63) / 64;
+    dim3 grid(((G + 4 * DW_WARPS - 1) / (4 * DW_WARPS)) * nchunk, (G + DW_TH - 1) / DW_TH, B);
+    rb_dw_kernel<<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk);
+    return (int)cudaGetLastError();
+}
+static int launch_pw(const __half* act, const __half* w2, const float* bias, __half* out, long long P, int Cp, int algo,
+                     cudaStream_t st) {
+    if (algo == 1) {
+        rb_pw_simt_kernel<<<(unsigned)P, 128, 0, st>>>(act, w2, bias, out, (size_t)P, Cp);
+        return (int)cudaGetLastError();
+    }
+    PwParams g;
+    g.bias = bias; g.out = out; g.P = P; g.Cp = Cp;
+    g.nsplit = (Cp + 255) / 256;
+    g.NT = pad16((Cp + g.nsplit - 1) / g.nsplit);
+    g.KA = (Cp + 63) / 64;
+    g.klast = (Cp - 64 * (g.KA - 1)) / 16;
+    const int stage_bytes = 128 * 128 + g.NT * 128;
+    g.nstage = max(2, min(PW_MAXSTAGE, (100 * 1024) / stage_bytes));
+    const long long mtiles = (P + 127) / 128;
+    if (mtiles * g.nsplit > 0x7fffffffLL) return GFB_EUNSUPPORTED;
+    g.nwork = (int)(mtiles * g.nsplit);
+    CUtensorMap tmA, tmB;
+    {   // fp16 pairs addressed as 32-bit words: inner extent Cp / 2, box 32 words = one 128-byte swizzle row
+        uint64_t dims[2] = {(uint64_t)Cp / 2, (uint64_t)P};
+        uint64_t strides[1] = {(uint64_t)Cp * 2};
+        uint32_t box[2] = {32u, 128u};
+        int rc = gfb_encode_tmap_f32(&tmA, act, 2, dims, strides, box, 3);
+        if (rc != GFB_OK) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)Cp / 2, (uint64_t)Cp};
+        uint64_t strides[1] = {(uint64_t)Cp * 2};
+        uint32_t box[2] = {32u, (uint32_t)g.NT};
+        int rc = gfb_encode_tmap_f32(&tmB, w2, 2, dims, strides, box, 3);
+        if (rc != GFB_OK) return rc;
+    }
+    const int smem = g.nstage * stage_bytes + 1024;
+    cudaError_t e = cudaFuncSetAttribute(rb_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)min((long long)g.nwork, (long long)2 * sms);
+    rb_pw_kernel<<<grid, PW_THREADS, smem, st>>>(tmA, tmB, g);
+    return (int)cudaGetLastError();
+}
+static int launch_out(const __half* act, const float* w, const float* bias, float* out, int B, int P, int Cp, int OC, cudaStream_t st) {
+    const long long total = (long long)B * P;
+    if (Cp <= 32) {
+        rb_out_kernel<16><<<(unsigned)((total + 15) / 16), 256, 0, st>>>(act, w, bias, out, B, P, Cp, OC);
+    } else {
+        rb_out_kernel<32><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(act, w, bias, out, B, P, Cp, OC);
+    }
+    return (int)cudaGetLastError();
+}
+
+// packed weights of one refiner (host-side packer: gfnet_b200/refiner.py): per block
+//   [wf 25*Cp f32][shift Cp f32][b2 Cp f32][w2 Cp*Cp f16]   then   [wout OC*Cp f32][bout 4 f32]
+static inline size_t block_bytes(int Cp) { return (size_t)27 * Cp * 4 + (size_t)Cp * Cp * 2; }
+
+}  // namespace rb
+}  // namespace gfb
+
+using namespace gfb;
+using namespace gfb::rb;
+
+#define RB_TRY(x) do { int rc__ = (x); if (rc__ != 0) return rc__; } while (0)
+
+extern "C" int gfb_refiner_pack_f16(const float* d, void* out, int B, int C, int P, gfb_stream_t stream) {
+    GFB_CHECK_ARG(d && out && B > 0 && B <= 65535 && C > 0 && P > 0);
+    return launch_pack(d, (__half*)out, B, C, pad16(C), P, gfb_cu(stream));
+}
+
+extern "C" int gfb_refiner_dw5_f16(const void* in, const float* wf, const float* shift, void* out, int B, int G, int Cp,
+                                   gfb_stream_t stream) {
+    GFB_CHECK_ARG(in && wf && shift && out && in != out && B > 0 && B <= 65535 && G > 0 && Cp > 0 && Cp % 16 == 0);
+    return launch_dw((const __half*)in, wf, shift, (__half*)out, B, G, Cp, gfb_cu(stream));
+}
+
+extern "C" int gfb_refiner_pw_f16(const void* act, const void* w2, const float* bias, void* out, long long P, int Cp, int algo,
+                                  gfb_stream_t stream) {
+    GFB_CHECK_ARG(act && w2 && bias && out && act != out && P > 0 && P < (1ll << 31) - 128 && Cp > 0 && Cp % 16 == 0 && Cp <= 512);
+    GFB_CHECK_ARG(algo == 0 || algo == 1);
+    if (!gfb_aligned(act, 16) || !gfb_aligned(w2, 16) || !gfb_aligned(out, 16) || !gfb_aligned(bias, 16)) return GFB_EALIGN;
+    return launch_pw((const __half*)act, (const __half*)w2, bias, (__half*)out, P, Cp, algo, gfb_cu(stream));
+}
+
+extern "C" int gfb_refiner_out_f32(const void* act, const float* w, const float* bias, float* out, int B, int P, int Cp, int OC,
+                                   gfb_stream_t stream) {
+    GFB_CHECK_ARG(act && w && bias && out && B > 0 && P > 0 && Cp > 0 && Cp % 16 == 0 && OC > 0 && OC <= 4);
+    return launch_out((const __half*)act, w, bias, out, B, P, Cp, OC, gfb_cu(stream));
+}
+
+extern "C" size_t gfb_refiner_blocks_weight_bytes(int C, int nblocks, int out_dim) {
+    const int Cp = pad16(C);
+    return (size_t)nblocks * block_bytes(Cp) + (size_t)out_dim * Cp * 4 + 16;
+}
+
+extern "C" int gfb_refiner_blocks_chunk(int B, int C, int G) {
+    // two activation buffers of a chunk inside ~48 MB of the 126 MB L2
+    const size_t per = (size_t)G * G * pad16(C) * 2;
+    size_t n = ((size_t)24 << 20) / per;
+    if (n < 1) n = 1;
+    if (n > (size_t)B) n = (size_t)B;
+    return (int)n;
+}
+
+extern "C" size_t gfb_refiner_blocks_workspace_bytes(int B, int C, int G, int chunk) {
+    if (chunk <= 0) chunk = gfb_refiner_blocks_chunk(B, C, G);
+    return 2 * (size_t)chunk * G * G * pad16(C) * 2 + 512;
+}
+
+// d [B,C,G,G] fp32 (the refiner input of model/network.py:555) -> out [B,out_dim,G,G] fp32 = out_conv(hidden_blocks(block1(d)))
+extern "C" int gfb_refiner_blocks_f16(const float* d, const void* weights, float* out, int B, int C, int G, int nblocks,
+                                      int out_dim, void* workspace, size_t ws_bytes, int chunk, int algo, gfb_stream_t stream) {
+    GFB_CHECK_ARG(d && weights && out && workspace && B > 0 && B <= 65535 && C > 0 && C <= 512 && G > 0 && G <= 4096);
+    GFB_CHECK_ARG(nblocks > 0 && out_dim > 0 && out_dim <= 4 && (algo == 0 || algo == 1));
+    if (chunk <= 0) chunk = gfb_refiner_blocks_chunk(B, C, G);
+    if (chunk > B) chunk = B;
+    if (ws_bytes < gfb_refiner_blocks_workspace_bytes(B, C, G, chunk)) return GFB_EWORKSPACE;
+    if (!gfb_aligned(weights, 16)) return GFB_EALIGN;
+    const int Cp = pad16(C), P = G * G;
+    cudaStream_t st = gfb_cu(stream);
+    unsigned char* ws = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    const size_t buf_bytes = (size_t)chunk * P * Cp * 2;
+    __half* h = reinterpret_cast<__half*>(ws);
+    __half* a = reinterpret_cast<__half*>(ws + buf_bytes);
+    const unsigned char* wb = reinterpret_cast<const unsigned char*>(weights);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = min(chunk, B - b0);
+        RB_TRY(launch_pack(d + (size_t)b0 * C * P, h, nb, C, Cp, P, st));
+        for (int k = 0; k < nblocks; ++k) {
+            const unsigned char* blk = wb + (size_t)k * block_bytes(Cp);
+            const float* wf = reinterpret_cast<const float*>(blk);
+            const float* shift = wf + 25 * Cp;
+            const float* b2 = shift + Cp;
+            const __half* w2 = reinterpret_cast<const __half*>(b2 + Cp);
+            RB_TRY(launch_dw(h, wf, shift, a, nb, G, Cp, st));
+            RB_TRY(launch_pw(a, w2, b2, h, (long long)nb * P, Cp, algo, st));
+        }
+        const float* wout = reinterpret_cast<const float*>(wb + (size_t)nblocks * block_bytes(Cp));
+        RB_TRY(launch_out(h, wout, wout + (size_t)out_dim * Cp, out + (size_t)b0 * out_dim * P, nb, P, Cp, out_dim, st));
+    }
+    return GFB_OK;
+}
+
+extern "C" int gfb_flow_update_f32(const float* delta, float* flow, float* certainty, float* disp_pre, int B, int G,
+                                   int scale, int H0, int W0, int zero_rule, gfb_stream_t stream) {
+    GFB_CHECK_ARG(delta && flow && certainty && disp_pre && B > 0 && G > 0 && H0 > 0 && W0 > 0);
+    const long long n = (long long)B * G * G;
+    flow_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, gfb_cu(stream)>>>(delta, flow, certainty, disp_pre, B, G * G,
+                                                                              (float)scale, 1.0f / (float)(4 * W0),
+                                                                              1.0f / (float)(4 * H0), zero_rule);
+    GFB_LAUNCH_RESULT();
+}
+
+extern "C" int gfb_upsample_bilinear_f32(const float* in, float* out, int planes, int Hi, int Wi, int Ho, int Wo,
+                                         gfb_stream_t stream) {
+    GFB_CHECK_ARG(in && out && in != out && planes > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0);
+    const long long n = (long long)planes * Ho * Wo;
+    upsample_bilinear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, gfb_cu(stream)>>>(in, out, planes, Hi, Wi, Ho, Wo,
+                                                                                    (float)Hi / (float)Ho, (float)Wi / (float)Wo);
+    GFB_LAUNCH_RESULT();
+}

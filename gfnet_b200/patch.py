@@ -6,13 +6,32 @@ replaced, not only utils.*; ``GFNet.corr_volume`` / ``pos_embed`` / ``sample`` a
 """
 import torch
 
-from . import ops, matcher
+from . import ops, matcher, refiner as _refiner
 
 
-def _refiner_forward(original):
+def _blocks_on_device(module):
+    """The packed convolution tail of a ConvRefiner, or None when the module is not the configuration the kernels cover
+    (dw=True, kernel_size=5, BatchNorm2d in eval mode, fp16 / bf16 autocast): decided once per module and mode."""
+    key = (module.training, bool(module.amp))
+    cached = getattr(module, "_gfb_blocks_state", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    rb = None
+    if not module.training and module.amp and module.amp_dtype in (torch.float16, torch.bfloat16):
+        try:
+            rb = _refiner.RefinerBlocks.from_module(module)
+        except NotImplementedError:
+            rb = None
+    module._gfb_blocks_state = (key, rb)
+    return rb
+
+
+def _refiner_forward(original, blocks=True):
     """ConvRefiner.forward (model/network.py:533-564) with lines 537-555 -- the two grid_samples, the displacement
     embedding, local_correlation and the concatenation -- replaced by ``ops.refiner_input`` (one buffer, written in
-    place); the convolution blocks (:557-562) stay the reference's own modules under the reference's autocast."""
+    place) and, with ``blocks``, the convolution tail (:557-563) by ``refiner.RefinerBlocks`` (fp16
+    activations like the reference's autocast, fp32 sums); otherwise the tail stays the reference's own modules under the
+    reference's autocast."""
     def forward(self, num_grid, x, y, flow, scale_factor=1, logits=None):
         if not (self.has_displacement_emb and self.corr_in_other and self.sample_mode == "bilinear" and x.is_cuda
                 and x.dtype == torch.float32 and y.dtype == torch.float32 and flow.dtype == torch.float32):
@@ -20,6 +39,10 @@ def _refiner_forward(original):
         r = self.local_corr_radius
         d = ops.refiner_input(num_grid, x, y, flow, self.disp_emb.weight, self.disp_emb.bias, r, scale_factor)
         local_corr = d[:, d.shape[1] - (2 * r + 1) ** 2:]
+        rb = _blocks_on_device(self) if blocks else None
+        if rb is not None:
+            h = rb(d)
+            return h[:, :2], h[:, 2:3], local_corr
         with torch.autocast("cuda", enabled=bool(self.amp), dtype=self.amp_dtype):
             h = self.block1(d)
             h = self.hidden_blocks(h)
@@ -28,9 +51,10 @@ def _refiner_forward(original):
     return forward
 
 
-def patch(network_module, utils_local_correlation=None, utils_kde=None, refiner=True):
+def patch(network_module, utils_local_correlation=None, utils_kde=None, refiner=True, refiner_blocks=True):
     """``patch(model.network)``; returns a dict of the originals so ``unpatch`` can restore them.  ``refiner=True`` also
-    replaces the input assembly of ``ConvRefiner.forward``."""
+    replaces the input assembly of ``ConvRefiner.forward``, ``refiner_blocks=True`` its convolution tail
+    (inference with the reference's autocast only, anything else keeps the reference's modules)."""
     saved = {
         "refiner_forward": network_module.ConvRefiner.forward,
         "local_correlation": network_module.local_correlation,
@@ -48,7 +72,7 @@ def patch(network_module, utils_local_correlation=None, utils_kde=None, refiner=
         return matcher.sample(matches, certainty, num, sample_mode=self.sample_mode, sample_thresh=self.sample_thresh)
     network_module.GFNet.sample = _sample
     if refiner:
-        network_module.ConvRefiner.forward = _refiner_forward(saved["refiner_forward"])
+        network_module.ConvRefiner.forward = _refiner_forward(saved["refiner_forward"], blocks=refiner_blocks)
     if utils_local_correlation is not None:
         utils_local_correlation.local_correlation = ops.local_correlation
     if utils_kde is not None:

@@ -128,6 +128,42 @@ int gfb_refiner_assemble_f32(const float* x, const float* y, const float* flow, 
 int gfb_local_corr_cat_f32(float* d, int Dtot, const float* f1, const float* flow,
                            int B, int C, int Hs, int Ws, int f1_pitch, int G, int r, int k_offset,
                            int phase, void* workspace, size_t workspace_bytes, gfb_stream_t stream);
+/* ---- refiner convolution blocks + decoder-loop glue ---------------------------
+ * replaces the tail of ConvRefiner.forward, model/network.py:557-563 (`d = block1(d); d = hidden_blocks(d)` under fp16
+ * autocast, `d = out_conv(d.float())`), each block = create_block :505-531 with dw=True: depth-wise 5x5 conv -> BatchNorm2d
+ * (eval) -> ReLU -> 1x1 conv.  Activations are fp16 NHWC [B, G*G, Cp] with Cp = C rounded up to 16 (pad channels zero), all
+ * sums accumulate in fp32 (the reference rounds to fp16 after every operator; stated tolerance in tests/test_refiner_blocks.py).
+ *   gfb_refiner_pack_f16   d [B,C,P] fp32 NCHW -> out [B,P,Cp] fp16
+ *   gfb_refiner_dw5_f16    out = relu(dwconv5x5(in) * bn_scale + shift): wf [25][Cp] fp32 (tap-major, bn_scale folded),
+ *                          shift [Cp] = (conv_bias - running_mean) * bn_scale + bn_bias; zero padding 2
+ *   gfb_refiner_pw_f16     out[p,n] = fp16(sum_k act[p,k] w2[n,k] + bias[n]); w2 [Cp][Cp] fp16; algo 0 = tcgen05 (TMA-fed,
+ *                          TMEM accumulator), 1 = CUDA-core cross-check; all pointers 16-byte aligned
+ *   gfb_refiner_out_f32    out [B,OC,P] fp32 = w [OC][Cp] . act + bias   (out_conv on d.float(), OC <= 4)
+ *   gfb_refiner_blocks_f16 the whole tail for d [B,C,G,G] -> out [B,out_dim,G,G], a batch chunk at a time so that the two
+ *                          activation buffers stay in L2 over the nblocks blocks; weights = the packed blob
+ *                          per block [wf 25*Cp f32][shift Cp f32][b2 Cp f32][w2 Cp*Cp f16], then [wout out_dim*Cp f32][bout 4 f32]
+ *                          (gfnet_b200/refiner.py packs it from a ConvRefiner); chunk 0 = gfb_refiner_blocks_chunk.
+ * gfb_flow_update_f32: the loop body model/network.py:265-274 for delta [B,3,G,G] = (dx, dy, d_certainty):
+ *   disp = int(scale) * (dx / (4 W0), dy / (4 H0)) evaluated as torch does on CUDA, zero_rule != 0: disp[|disp - pre| / |pre|
+ *   < 1e-6] = 0 (:270-271, eval mode), flow += disp, certainty += d_certainty, disp_pre = disp.
+ * gfb_upsample_bilinear_f32: F.interpolate(x, size=(Ho,Wo), mode="bilinear", align_corners=False) on [planes,Hi,Wi]
+ *   (:238-249, 276-285). */
+int gfb_refiner_pack_f16(const float* d, void* out, int B, int C, int P, gfb_stream_t stream);
+int gfb_refiner_dw5_f16(const void* in, const float* wf, const float* shift, void* out, int B, int G, int Cp,
+                        gfb_stream_t stream);
+int gfb_refiner_pw_f16(const void* act, const void* w2, const float* bias, void* out, long long P, int Cp, int algo,
+                       gfb_stream_t stream);
+int gfb_refiner_out_f32(const void* act, const float* w, const float* bias, float* out, int B, int P, int Cp, int OC,
+                        gfb_stream_t stream);
+size_t gfb_refiner_blocks_weight_bytes(int C, int nblocks, int out_dim);
+int gfb_refiner_blocks_chunk(int B, int C, int G);
+size_t gfb_refiner_blocks_workspace_bytes(int B, int C, int G, int chunk);
+int gfb_refiner_blocks_f16(const float* d, const void* weights, float* out, int B, int C, int G, int nblocks,
+                           int out_dim, void* workspace, size_t workspace_bytes, int chunk, int algo, gfb_stream_t stream);
+int gfb_flow_update_f32(const float* delta, float* flow, float* certainty, float* disp_pre, int B, int G,
+                        int scale, int H0, int W0, int zero_rule, gfb_stream_t stream);
+int gfb_upsample_bilinear_f32(const float* in, float* out, int planes, int Hi, int Wi, int Ho, int Wo,
+                              gfb_stream_t stream);
 /* how many (pre-pass, main) launch pairs one gfb_local_corr_tc2_f32 call issues for these shapes */
 int gfb_local_corr_tc2_groups(int B, int C, int Hs, int Ws, int G, int group);
 /* F.avg_pool2d(x, 2, 2) on [N,H,W] planes -> [N,H/2,W/2] (local_correlation.py:71). */
