@@ -372,6 +372,12 @@ def run_ours(args):
                 gpu_ref = gpu_reference_run(synth, args, dev)
             except Exception as exc:                   # secondary figure: never fail the bench line over it
                 gpu_ref = {"unavailable": repr(exc)[:200]}
+        tail = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                tail = refiner_tail_run(synth, args, B, dev)
+            except Exception as exc:
+                tail = {"unavailable": repr(exc)[:200]}
         line = {"metric": metric_name(args, synth), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": CONFIGS[args.config][1], "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(args, world, B, synth),
@@ -379,11 +385,51 @@ def run_ours(args):
                 "clocks": clocks, "gpu_launches": hp.kernel_launches(batch) * args.steps,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                         "overlap": "upload of step i+1 on a copy stream while step i computes (two device input sets)"},
-                "pipelined": pipelined, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": gpu_ref,
+                "pipelined": pipelined, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": gpu_ref, "refiner_tail": tail,
                 "ace_px_mean": float(out["err"].mean()), "solved": int(out["status"].sum())}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def refiner_tail_run(synth, args, B, dev):
+    """Extra key (outside the BASELINE metric): the refiner convolution tails (model/network.py:557-563) a step of
+    the reference's decoder would run between the correlation calls -- one RefinerBlocks call per scale and pass at op batch 2B,
+    random-init weights, times num_itr.  Scale 1 (no local correlation, model/network.py:139-153) included."""
+    import torch
+    from gfnet_b200 import refiner as RF
+    res, up = CONFIGS[args.config][0]
+    ddim = {16: 64, 8: 64, 4: 32, 2: 16, 1: 8}
+    shapes = []
+    for pi, u in enumerate((None, up) if up else (None,)):
+        for (s, c, hs, G, r) in synth.pyramid_config(res, upsample_res=u):
+            shapes.append((f"pass{pi + 1}_scale{s}", 2 * c + ddim[s] + (2 * r + 1) ** 2, G))
+        shapes.append((f"pass{pi + 1}_scale1", 2 * 8 + ddim[1], synth.final_grid(res, u) if u else 8 * (res // 14)))
+    tot_ms, tot_flops, launches, rows = 0.0, 0.0, 0, {}
+    for name, c, G in shapes:
+        torch.manual_seed(c)
+        blocks = [torch.nn.Sequential(torch.nn.Conv2d(c, c, 5, 1, 2, groups=c), torch.nn.BatchNorm2d(c), torch.nn.ReLU(inplace=True),
+                                      torch.nn.Conv2d(c, c, 1, 1, 0)).to(dev).eval() for _ in range(9)]
+        rb = RF.RefinerBlocks(blocks, torch.nn.Conv2d(c, 3, 1, 1, 0).to(dev).eval())
+        d = torch.randn(2 * B, c, G, G, device=dev)
+        rb(d)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            rb(d)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 2
+        rows[name] = {"C": c, "G": G, "ms": ms, "tflops": RF.refiner_blocks_flops(2 * B, c, G) / ms * 1e-9}
+        tot_ms += ms * NUM_ITR
+        tot_flops += RF.refiner_blocks_flops(2 * B, c, G) * NUM_ITR
+        launches += rb.launches(2 * B, G) * NUM_ITR
+        del rb, d, blocks
+    return {"what": "9 blocks of depth-wise 5x5 + batch norm + ReLU + 1x1 convolution, then out_conv, per scale / pass / iteration "
+                    "(fp16 activations, fp32 sums); not part of `value`", "ms_per_step": tot_ms, "tflops": tot_flops / tot_ms * 1e-9,
+            "launches_per_step": launches, "by_scale": rows}
+
 
 
 def main():

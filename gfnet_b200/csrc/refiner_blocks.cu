@@ -70,15 +70,21 @@ __global__ void __launch_bounds__(256) rb_pack_kernel(const float* __restrict__ 
 constexpr int DW_TH = 16;      // output rows per strip ((DW_TH + 4) % 5 == 0)
 constexpr int DW_WARPS = 4;    // neighbouring strips of one channel chunk: their x halos meet in L1
 
-__global__ void __launch_bounds__(DW_WARPS * 32) rb_dw_kernel(const __half* __restrict__ in, const float* __restrict__ wf,
-                                                              const float* __restrict__ shift, __half* __restrict__ out,
-                                                              int G, int Cp, int nchunk) {
+// lp = channel pairs per chunk (8, 16 or 32 lanes); the other 32 / lp lane groups of a warp take neighbouring strips, so that
+// narrow refiners (Cp = 32, 80) keep every lane busy.
+// CP = the channel pitch as a compile-time constant for the refiners GFNet builds (every tap / pixel offset an immediate: the
+// run-time pitch spent 120 of 320 instructions per input row on 64-bit addresses), 0 = run-time pitch.
+template <int CP>
+__global__ void __launch_bounds__(DW_WARPS * 32, 3) rb_dw_kernel(const __half* __restrict__ in, const float* __restrict__ wf,
+                                                                 const float* __restrict__ shift, __half* __restrict__ out,
+                                                                 int G, int Cp_rt, int nchunk, int lp) {
+    const int Cp = CP ? CP : Cp_rt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunk = blockIdx.x % nchunk, xs = blockIdx.x / nchunk;
-    const int c = (chunk * 32 + lane) * 2;
-    const int x0 = (xs * DW_WARPS + warp) * 4, y0 = blockIdx.y * DW_TH, b = blockIdx.z;
-    if (x0 >= G) return;
-    const bool cok = c < Cp;
+    const int spw = 32 / lp;                                          // strips per warp
+    const int c = (chunk * lp + lane % lp) * 2;
+    const int x0 = ((xs * DW_WARPS + warp) * spw + lane / lp) * 4, y0 = blockIdx.y * DW_TH, b = blockIdx.z;
+    const bool cok = c < Cp && x0 < G;
     unsigned long long w[25];
 #pragma unroll
     for (int t = 0; t < 25; ++t) w[t] = cok ? pack2(__ldg(wf + t * Cp + c), __ldg(wf + t * Cp + c + 1)) : 0ull;
@@ -94,20 +100,31 @@ __global__ void __launch_bounds__(DW_WARPS * 32) rb_dw_kernel(const __half* __re
 #pragma unroll
     for (int i = 0; i < 8; ++i) xok[i] = cok && x0 - 2 + i >= 0 && x0 - 2 + i < G;
 
+    // the loads of input row j + 1 are issued before the arithmetic of row j (one row of look-ahead per warp)
+    uint32_t raw[8];
+    const __half* row = inb + ((long long)(y0 - 2) * G + (x0 - 2)) * Cp;      // walks down one image row per input row
+    const long long row_pitch = (long long)G * Cp;
+    auto load_row = [&](int j) {
+        const int iy = y0 - 2 + j;
+        const bool yok = iy >= 0 && iy < G && j < DW_TH + 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            raw[i] = 0u;
+            if (yok && xok[i]) raw[i] = __ldg(reinterpret_cast<const uint32_t*>(row + i * Cp));
+        }
+        row += row_pitch;
+    };
+    load_row(0);
+    __half* orow = outb + ((long long)(y0 - 4) * G + x0) * Cp;               // output row j - 4
 #pragma unroll 1
     for (int base = 0; base < DW_TH + 4; base += 5) {
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
-            const int j = base + s, iy = y0 - 2 + j;
+            const int j = base + s;
             unsigned long long v[8];
-            const bool yok = iy >= 0 && iy < G;
-            const __half* row = inb + ((size_t)iy * G + (x0 - 2)) * Cp;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint32_t h = 0u;
-                if (yok && xok[i]) h = __ldg(reinterpret_cast<const uint32_t*>(row + (size_t)i * Cp));
-                v[i] = h2_to_f2(h);
-            }
+            for (int i = 0; i < 8; ++i) v[i] = h2_to_f2(raw[i]);
+            load_row(j + 1);
 #pragma unroll
             for (int ky = 0; ky < 5; ++ky) {
                 const int slot = (s - ky + 5) % 5;       // output row j - ky
@@ -123,10 +140,10 @@ __global__ void __launch_bounds__(DW_WARPS * 32) rb_dw_kernel(const __half* __re
                 for (int p = 0; p < 4; ++p) {
                     const float2 a = unpack2(acc[slot][p]);
                     if (x0 + p < G)
-                        *reinterpret_cast<uint32_t*>(outb + ((size_t)oy * G + x0 + p) * Cp) =
-                            f2_to_h2(fmaxf(a.x + sh0, 0.f), fmaxf(a.y + sh1, 0.f));
+                        *reinterpret_cast<uint32_t*>(orow + p * Cp) = f2_to_h2(fmaxf(a.x + sh0, 0.f), fmaxf(a.y + sh1, 0.f));
                 }
             }
+            orow += row_pitch;
 #pragma unroll
             for (int p = 0; p < 4; ++p) acc[slot][p] = 0ull;
         }
@@ -398,9 +415,20 @@ static int launch_pack(const float* d, __half* out, int B, int C, int Cp, int P,
     return (int)cudaGetLastError();
 }
 static int launch_dw(const __half* in, const float* wf, const float* shift, __half* out, int B, int G, int Cp, cudaStream_t st) {
-    const int nchunk = (Cp + 63) / 64;
-    dim3 grid(((G + 4 * DW_WARPS - 1) / (4 * DW_WARPS)) * nchunk, (G + DW_TH - 1) / DW_TH, B);
-    rb_dw_kernel<<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk);
+    // lanes per chunk: the widest of 32 / 16 / 8 channel pairs that wastes at most ~5 % of the lanes on channel padding
+    const int pairs = Cp / 2;
+    int lp = 32;
+    while (lp > 8 && ((pairs + lp - 1) / lp) * lp * 20 > pairs * 21) lp /= 2;
+    const int nchunk = (pairs + lp - 1) / lp, spw = 32 / lp;
+    dim3 grid(((G + 4 * DW_WARPS * spw - 1) / (4 * DW_WARPS * spw)) * nchunk, (G + DW_TH - 1) / DW_TH, B);
+    switch (Cp) {
+        case 32: rb_dw_kernel<32><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
+        case 80: rb_dw_kernel<80><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
+        case 192: rb_dw_kernel<192><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
+        case 368: rb_dw_kernel<368><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
+        case 432: rb_dw_kernel<432><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
+        default: rb_dw_kernel<0><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
+    }
     return (int)cudaGetLastError();
 }
 static int launch_pw(const __half* act, const __half* w2, const float* bias, __half* out, long long P, int Cp, int algo,
@@ -436,12 +464,19 @@ static int launch_pw(const __half* act, const __half* w2, const float* bias, __h
         if (rc != GFB_OK) return rc;
     }
     const int smem = g.nstage * stage_bytes + 1024;
-    cudaError_t e = cudaFuncSetAttribute(rb_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    int dev = 0, sms = 148;
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = (int)min((long long)g.nwork, (long long)2 * sms);
+    static int sms_of[64] = {0};           // immutable per-device cache (SM count; the attribute is set once per device)
+    if (dev < 0 || dev >= 64) return GFB_EUNSUPPORTED;
+    if (sms_of[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(rb_pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        int sms = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess || sms <= 0) return e != cudaSuccess ? (int)e : GFB_ENODEVICE;
+        sms_of[dev] = sms;
+    }
+    const int grid = (int)min((long long)g.nwork, (long long)2 * sms_of[dev]);
     rb_pw_kernel<<<grid, PW_THREADS, smem, st>>>(tmA, tmB, g);
     return (int)cudaGetLastError();
 }
@@ -503,7 +538,8 @@ extern "C" int gfb_refiner_blocks_chunk(int B, int C, int G) {
     size_t n = ((size_t)24 << 20) / per;
     if (n < 1) n = 1;
     if (n > (size_t)B) n = (size_t)B;
-    return (int)n;
+    const size_t nchunks = ((size_t)B + n - 1) / n;          // equal chunks: no short tail chunk that under-fills the SMs
+    return (int)(((size_t)B + nchunks - 1) / nchunks);
 }
 
 extern "C" size_t gfb_refiner_blocks_workspace_bytes(int B, int C, int G, int chunk) {
