@@ -12,8 +12,8 @@
 //   rb_pw_kernel     the 1x1 convolution as a GEMM on tcgen05: A = 128 pixels x K (TMA, 128B swizzle), B = W2 rows (TMA),
 //                    fp32 accumulator in TMEM, epilogue adds the bias and writes fp16 NHWC; persistent over pixel tiles
 //   rb_out_kernel    out_conv (hidden -> 3) in fp32, NCHW output
-// gfb_refiner_blocks_f16 runs the chain for a batch chunk at a time so that the two ping-pong activation buffers of a chunk
-// stay in the 126 MB L2 across all nine blocks: HBM sees the refiner input once and the three output planes once.
+// gfb_refiner_blocks_f16 runs the chain over two ping-pong activation buffers (the whole batch at once; `chunk` bounds the
+// buffers: L2-sized chunks were measured slower, see gfb_refiner_blocks_chunk).
 #include "common.cuh"
 #include <cuda_fp16.h>
 
@@ -64,10 +64,10 @@ __global__ void __launch_bounds__(256) rb_pack_kernel(const float* __restrict__ 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // depth-wise 5x5 (zero padding 2) + folded batch norm + ReLU on NHWC fp16.  wf [25][Cp] fp32 = tap * bn_scale, shift [Cp] =
-// (conv_bias - running_mean) * bn_scale + bn_bias.  A warp = 64 channels (lane = channel pair) x a strip of 4 x DW_TH outputs;
+// (conv_bias - running_mean) * bn_scale + bn_bias.  A warp = 64 channels (lane = channel pair) x a strip of 4 x th outputs;
 // input row j of the strip feeds the five output rows j-4..j, whose accumulators live in a register ring (static slots: the
 // row loop is unrolled by five).
-constexpr int DW_TH = 16;      // output rows per strip ((DW_TH + 4) % 5 == 0)
+constexpr int DW_TH_MIN = 16;  // output rows per strip: run-time `th` with (th + 4) % 5 == 0, chosen by launch_dw
 constexpr int DW_WARPS = 4;    // neighbouring strips of one channel chunk: their x halos meet in L1
 
 // lp = channel pairs per chunk (8, 16 or 32 lanes); the other 32 / lp lane groups of a warp take neighbouring strips, so that
@@ -77,13 +77,13 @@ constexpr int DW_WARPS = 4;    // neighbouring strips of one channel chunk: thei
 template <int CP>
 __global__ void __launch_bounds__(DW_WARPS * 32, 3) rb_dw_kernel(const __half* __restrict__ in, const float* __restrict__ wf,
                                                                  const float* __restrict__ shift, __half* __restrict__ out,
-                                                                 int G, int Cp_rt, int nchunk, int lp) {
+                                                                 int G, int Cp_rt, int nchunk, int lp, int th) {
     const int Cp = CP ? CP : Cp_rt;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunk = blockIdx.x % nchunk, xs = blockIdx.x / nchunk;
     const int spw = 32 / lp;                                          // strips per warp
     const int c = (chunk * lp + lane % lp) * 2;
-    const int x0 = ((xs * DW_WARPS + warp) * spw + lane / lp) * 4, y0 = blockIdx.y * DW_TH, b = blockIdx.z;
+    const int x0 = ((xs * DW_WARPS + warp) * spw + lane / lp) * 4, y0 = blockIdx.y * th, b = blockIdx.z;
     const bool cok = c < Cp && x0 < G;
     unsigned long long w[25];
 #pragma unroll
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(DW_WARPS * 32, 3) rb_dw_kernel(const __half* _
     const long long row_pitch = (long long)G * Cp;
     auto load_row = [&](int j) {
         const int iy = y0 - 2 + j;
-        const bool yok = iy >= 0 && iy < G && j < DW_TH + 4;
+        const bool yok = iy >= 0 && iy < G && j < th + 4;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             raw[i] = 0u;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(DW_WARPS * 32, 3) rb_dw_kernel(const __half* _
     load_row(0);
     __half* orow = outb + ((long long)(y0 - 4) * G + x0) * Cp;               // output row j - 4
 #pragma unroll 1
-    for (int base = 0; base < DW_TH + 4; base += 5) {
+    for (int base = 0; base < th + 4; base += 5) {
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
             const int j = base + s;
@@ -235,15 +235,17 @@ __global__ void __launch_bounds__(PW_THREADS, 2) rb_pw_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap tmB, const PwParams g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t full[PW_MAXSTAGE], empty[PW_MAXSTAGE], d_full[2], d_empty[2];
+    __shared__ uint64_t full[PW_MAXSTAGE], empty[PW_MAXSTAGE], d_full[4], d_empty[4];
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias_s[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)g.NT * 128, stage_bytes = a_bytes + b_bytes;
-    const int nacc = g.NT <= 128 ? 2 : 1;
+    // accumulators in flight (256 TMEM columns): narrow tiles are latency-bound per tile, so keep up to four going
+    const uint32_t nacc = g.NT <= 64 ? 4 : g.NT <= 128 ? 2 : 1, acc_cols = PW_TMEM / nacc;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], 4); }
+        for (int a = 0; a < 4; ++a) { mbar_init(&d_full[a], 1); mbar_init(&d_empty[a], 4); }
         mbar_fence_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) rb_pw_kernel(const __grid_const
                 const uint32_t a = t % nacc;
                 mbar_wait(&d_empty[a], ((t / nacc) & 1) ^ 1);
                 fence_after_sync();
-                const uint32_t dt = tmem_base + a * 128u;
+                const uint32_t dt = tmem_base + a * acc_cols;
                 uint32_t accum = 0;
                 for (int ka = 0; ka < g.KA; ++ka, ++it) {
                     const uint32_t s = it % g.nstage;
@@ -297,8 +299,16 @@ __global__ void __launch_bounds__(PW_THREADS, 2) rb_pw_kernel(const __grid_const
     } else {
         const int q = warp & 3;                        // TMEM lane quarter this warp may read
         uint32_t t = 0;
+        int half_s = -1;
         for (int wk = blockIdx.x; wk < g.nwork; wk += gridDim.x, ++t) {
             const int half = wk % g.nsplit, mt = wk / g.nsplit;
+            if (half != half_s) {                      // the bias of this N tile (a CTA keeps its tile: the grid is even)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int e = threadIdx.x - 64;
+                for (int n = e; n < g.NT; n += 128) bias_s[n] = half * g.NT + n < g.Cp ? __ldg(g.bias + half * g.NT + n) : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                half_s = half;
+            }
             const uint32_t a = t % nacc;
             mbar_wait(&d_full[a], (t / nacc) & 1);
             fence_after_sync();
@@ -307,15 +317,15 @@ __global__ void __launch_bounds__(PW_THREADS, 2) rb_pw_kernel(const __grid_const
             const int nchunks = (g.NT + 31) / 32;
             for (int ch = 0; ch < nchunks; ++ch) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 128u + (uint32_t)ch * 32u, r);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * acc_cols + (uint32_t)ch * 32u, r);
                 tmem_ld_wait();
                 const int n0 = half * g.NT + ch * 32;
 #pragma unroll
                 for (int v8 = 0; v8 < 4; ++v8) {
                     const int n = n0 + v8 * 8;
                     if (ch * 32 + v8 * 8 < g.NT && n < g.Cp && p < g.P) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + n + 4));
+                        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + v8 * 8);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch * 32 + v8 * 8 + 4);
                         uint4 o;
                         o.x = f2_to_h2(__uint_as_float(r[v8 * 8 + 0]) + b0.x, __uint_as_float(r[v8 * 8 + 1]) + b0.y);
                         o.y = f2_to_h2(__uint_as_float(r[v8 * 8 + 2]) + b0.z, __uint_as_float(r[v8 * 8 + 3]) + b0.w);
@@ -420,14 +430,24 @@ static int launch_dw(const __half* in, const float* wf, const float* shift, __ha
     int lp = 32;
     while (lp > 8 && ((pairs + lp - 1) / lp) * lp * 20 > pairs * 21) lp /= 2;
     const int nchunk = (pairs + lp - 1) / lp, spw = 32 / lp;
-    dim3 grid(((G + 4 * DW_WARPS * spw - 1) / (4 * DW_WARPS * spw)) * nchunk, (G + DW_TH - 1) / DW_TH, B);
+    const int xblocks = (G + 4 * DW_WARPS * spw - 1) / (4 * DW_WARPS * spw);
+    // strip height: every strip re-reads 4 halo rows, so taller strips cost less -- as long as the grid still fills the SMs
+    // (3 blocks per SM, at least two waves) and the last strip of a column is not mostly empty
+    int th = DW_TH_MIN;
+    long long best = (long long)((G + th - 1) / th) * (th + 4);
+    for (int t = DW_TH_MIN + 5; t <= G + 4; t += 5) {
+        const int segs = (G + t - 1) / t;
+        if ((long long)xblocks * nchunk * segs * B < 2 * 3 * 148) break;
+        if ((long long)segs * (t + 4) < best) { best = (long long)segs * (t + 4); th = t; }
+    }
+    dim3 grid(xblocks * nchunk, (G + th - 1) / th, B);
     switch (Cp) {
-        case 32: rb_dw_kernel<32><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
-        case 80: rb_dw_kernel<80><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
-        case 192: rb_dw_kernel<192><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
-        case 368: rb_dw_kernel<368><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
-        case 432: rb_dw_kernel<432><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
-        default: rb_dw_kernel<0><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp); break;
+        case 32: rb_dw_kernel<32><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp, th); break;
+        case 80: rb_dw_kernel<80><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp, th); break;
+        case 192: rb_dw_kernel<192><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp, th); break;
+        case 368: rb_dw_kernel<368><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp, th); break;
+        case 432: rb_dw_kernel<432><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp, th); break;
+        default: rb_dw_kernel<0><<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, out, G, Cp, nchunk, lp, th); break;
     }
     return (int)cudaGetLastError();
 }
@@ -533,12 +553,13 @@ extern "C" size_t gfb_refiner_blocks_weight_bytes(int C, int nblocks, int out_di
 }
 
 extern "C" int gfb_refiner_blocks_chunk(int B, int C, int G) {
-    // two activation buffers of a chunk inside ~48 MB of the 126 MB L2
+    // The whole batch at once unless an activation buffer would exceed 1 GiB.  Chunks sized for the L2 (two 24 MB buffers) were
+    // measured 25-45 % slower at op batch 64: short grids lose to wave quantisation and the kernels are not HBM-bound.
     const size_t per = (size_t)G * G * pad16(C) * 2;
-    size_t n = ((size_t)24 << 20) / per;
+    size_t n = ((size_t)1 << 30) / per;
     if (n < 1) n = 1;
     if (n > (size_t)B) n = (size_t)B;
-    const size_t nchunks = ((size_t)B + n - 1) / n;          // equal chunks: no short tail chunk that under-fills the SMs
+    const size_t nchunks = ((size_t)B + n - 1) / n;          // equal chunks
     return (int)(((size_t)B + nchunks - 1) / nchunks);
 }
 
