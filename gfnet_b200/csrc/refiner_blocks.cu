@@ -215,6 +215,96 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// mma.sync version for narrow refiners (Cp <= 96: scales 2 and 1) -----------------------------------------------------------
+// With K = N <= 96 the 1x1 convolution is a streaming operation (arithmetic intensity <= 48 flop/B): the tcgen05 kernel spends
+// its time on per-tile hand-offs (TMA -> MMA -> TMEM -> registers) of 8-20 KB tiles.  Here a warp owns 16 pixels at a time and
+// nothing is staged: a lane's coalesced 16-byte loads of the NHWC rows ARE its A fragments, and its D fragments ARE 16-byte
+// row segments, because the k and n orders of the MMA are permuted consistently in the (shared-memory) weight fragments:
+//   lane (g = lane / 4, t = lane % 4), load l, half u:   k-slot 2t + e   <->  channel 32 l + 8 t + 4 u + e
+//                                                        k-slot 2t + 8 + e <->  channel 32 l + 8 t + 4 u + 2 + e
+//   n-tile (q, j), column n                              <->  output channel 32 q + 8 (n / 2) + 2 j + n % 2
+// so that over j = 0..3 lane t holds output channels 32 q + 8 t .. + 7 of rows g and g + 8.
+__device__ __forceinline__ void mma_m16n8k16_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                 uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int PWM_THREADS = 128;
+
+template <int KL>      // 32-channel groups: Cp <= 32 KL
+__global__ void __launch_bounds__(PWM_THREADS, 4) rb_pw_mma_kernel(const __half* __restrict__ act, const __half* __restrict__ w2,
+                                                                   const float* __restrict__ bias, __half* __restrict__ out,
+                                                                   long long P, int Cp) {
+    __shared__ uint2 wfrag[KL * 2 * KL * 4][32];            // [(l, u, q, j)][lane] = (b0, b1)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    for (int i = threadIdx.x; i < KL * 2 * KL * 4 * 32; i += PWM_THREADS) {
+        const int L = i & 31, f = i >> 5, j = f & 3, q = (f >> 2) % KL, u = (f / (4 * KL)) & 1, l = f / (8 * KL);
+        const int co = 32 * q + 8 * ((L >> 2) >> 1) + 2 * j + ((L >> 2) & 1), ch = 32 * l + 8 * (L & 3) + 4 * u;
+        uint2 v = make_uint2(0u, 0u);
+        if (co < Cp && ch < Cp) v = __ldg(reinterpret_cast<const uint2*>(w2 + (size_t)co * Cp + ch));
+        wfrag[f][L] = v;
+    }
+    float bs[KL][8];
+#pragma unroll
+    for (int q = 0; q < KL; ++q)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bs[q][e] = 32 * q + 8 * t + e < Cp ? __ldg(bias + 32 * q + 8 * t + e) : 0.f;
+    __syncthreads();
+
+    const long long nblk = (P + 15) / 16;
+    for (long long blk = (long long)blockIdx.x * (PWM_THREADS / 32) + warp; blk < nblk; blk += (long long)gridDim.x * (PWM_THREADS / 32)) {
+        const long long r0 = blk * 16 + g, r1 = r0 + 8;
+        uint4 alo[KL], ahi[KL];
+#pragma unroll
+        for (int l = 0; l < KL; ++l) {
+            alo[l] = make_uint4(0u, 0u, 0u, 0u);
+            ahi[l] = make_uint4(0u, 0u, 0u, 0u);
+            if (32 * l + 8 * t < Cp) {
+                if (r0 < P) alo[l] = __ldcs(reinterpret_cast<const uint4*>(act + (size_t)r0 * Cp + 32 * l + 8 * t));
+                if (r1 < P) ahi[l] = __ldcs(reinterpret_cast<const uint4*>(act + (size_t)r1 * Cp + 32 * l + 8 * t));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KL; ++q) {
+            float acc[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+#pragma unroll
+            for (int l = 0; l < KL; ++l) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint2 b_u0 = wfrag[((l * 2 + 0) * KL + q) * 4 + j][lane];
+                    const uint2 b_u1 = wfrag[((l * 2 + 1) * KL + q) * 4 + j][lane];
+                    mma_m16n8k16_f16(acc[j], alo[l].x, ahi[l].x, alo[l].y, ahi[l].y, b_u0.x, b_u0.y);
+                    mma_m16n8k16_f16(acc[j], alo[l].z, ahi[l].z, alo[l].w, ahi[l].w, b_u1.x, b_u1.y);
+                }
+            }
+            if (32 * q + 8 * t < Cp) {
+                uint4 o0, o1;
+                o0.x = f2_to_h2(acc[0][0] + bs[q][0], acc[0][1] + bs[q][1]); o1.x = f2_to_h2(acc[0][2] + bs[q][0], acc[0][3] + bs[q][1]);
+                o0.y = f2_to_h2(acc[1][0] + bs[q][2], acc[1][1] + bs[q][3]); o1.y = f2_to_h2(acc[1][2] + bs[q][2], acc[1][3] + bs[q][3]);
+                o0.z = f2_to_h2(acc[2][0] + bs[q][4], acc[2][1] + bs[q][5]); o1.z = f2_to_h2(acc[2][2] + bs[q][4], acc[2][3] + bs[q][5]);
+                o0.w = f2_to_h2(acc[3][0] + bs[q][6], acc[3][1] + bs[q][7]); o1.w = f2_to_h2(acc[3][2] + bs[q][6], acc[3][3] + bs[q][7]);
+                if (r0 < P) *reinterpret_cast<uint4*>(out + (size_t)r0 * Cp + 32 * q + 8 * t) = o0;
+                if (r1 < P) *reinterpret_cast<uint4*>(out + (size_t)r1 * Cp + 32 * q + 8 * t) = o1;
+            }
+        }
+    }
+}
+
+template <int KL>
+static int launch_pw_mma(const __half* act, const __half* w2, const float* bias, __half* out, long long P, int Cp, cudaStream_t st) {
+    const long long nblk = (P + 15) / 16;
+    const long long want = (nblk + PWM_THREADS / 32 - 1) / (PWM_THREADS / 32);
+    const int grid = (int)min(want, (long long)148 * 4);              // one resident wave (4 blocks per SM): the weight fragments
+                                                                      // are built once per block, warps stride over the pixels
+    rb_pw_mma_kernel<KL><<<grid, PWM_THREADS, 0, st>>>(act, w2, bias, out, P, Cp);
+    return (int)cudaGetLastError();
+}
+
 struct PwParams {
     const float* bias;
     __half* out;
@@ -457,6 +547,11 @@ static int launch_pw(const __half* act, const __half* w2, const float* bias, __h
         rb_pw_simt_kernel<<<(unsigned)P, 128, 0, st>>>(act, w2, bias, out, (size_t)P, Cp);
         return (int)cudaGetLastError();
     }
+    if (algo == 0 && Cp <= 96) {                 // narrow refiners: the streaming mma.sync kernel
+        if (Cp <= 32) return launch_pw_mma<1>(act, w2, bias, out, P, Cp, st);
+        if (Cp <= 64) return launch_pw_mma<2>(act, w2, bias, out, P, Cp, st);
+        return launch_pw_mma<3>(act, w2, bias, out, P, Cp, st);
+    }
     PwParams g;
     g.bias = bias; g.out = out; g.P = P; g.Cp = Cp;
     g.nsplit = (Cp + 255) / 256;
@@ -536,7 +631,7 @@ extern "C" int gfb_refiner_dw5_f16(const void* in, const float* wf, const float*
 extern "C" int gfb_refiner_pw_f16(const void* act, const void* w2, const float* bias, void* out, long long P, int Cp, int algo,
                                   gfb_stream_t stream) {
     GFB_CHECK_ARG(act && w2 && bias && out && act != out && P > 0 && P < (1ll << 31) - 128 && Cp > 0 && Cp % 16 == 0 && Cp <= 512);
-    GFB_CHECK_ARG(algo == 0 || algo == 1);
+    GFB_CHECK_ARG(algo >= 0 && algo <= 2);
     if (!gfb_aligned(act, 16) || !gfb_aligned(w2, 16) || !gfb_aligned(out, 16) || !gfb_aligned(bias, 16)) return GFB_EALIGN;
     return launch_pw((const __half*)act, (const __half*)w2, bias, (__half*)out, P, Cp, algo, gfb_cu(stream));
 }
@@ -572,7 +667,7 @@ extern "C" size_t gfb_refiner_blocks_workspace_bytes(int B, int C, int G, int ch
 extern "C" int gfb_refiner_blocks_f16(const float* d, const void* weights, float* out, int B, int C, int G, int nblocks,
                                       int out_dim, void* workspace, size_t ws_bytes, int chunk, int algo, gfb_stream_t stream) {
     GFB_CHECK_ARG(d && weights && out && workspace && B > 0 && B <= 65535 && C > 0 && C <= 512 && G > 0 && G <= 4096);
-    GFB_CHECK_ARG(nblocks > 0 && out_dim > 0 && out_dim <= 4 && (algo == 0 || algo == 1));
+    GFB_CHECK_ARG(nblocks > 0 && out_dim > 0 && out_dim <= 4 && algo >= 0 && algo <= 2);
     if (chunk <= 0) chunk = gfb_refiner_blocks_chunk(B, C, G);
     if (chunk > B) chunk = B;
     if (ws_bytes < gfb_refiner_blocks_workspace_bytes(B, C, G, chunk)) return GFB_EWORKSPACE;

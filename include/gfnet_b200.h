@@ -136,11 +136,12 @@ int gfb_local_corr_cat_f32(float* d, int Dtot, const float* f1, const float* flo
  *   gfb_refiner_pack_f16   d [B,C,P] fp32 NCHW -> out [B,P,Cp] fp16
  *   gfb_refiner_dw5_f16    out = relu(dwconv5x5(in) * bn_scale + shift): wf [25][Cp] fp32 (tap-major, bn_scale folded),
  *                          shift [Cp] = (conv_bias - running_mean) * bn_scale + bn_bias; zero padding 2
- *   gfb_refiner_pw_f16     out[p,n] = fp16(sum_k act[p,k] w2[n,k] + bias[n]); w2 [Cp][Cp] fp16; algo 0 = tcgen05 (TMA-fed,
- *                          TMEM accumulator), 1 = CUDA-core cross-check; all pointers 16-byte aligned
+ *   gfb_refiner_pw_f16     out[p,n] = fp16(sum_k act[p,k] w2[n,k] + bias[n]); w2 [Cp][Cp] fp16; algo 0 = auto (Cp <= 96: streaming
+ *                          mma.sync kernel, above: tcgen05, TMA-fed, TMEM accumulator), 2 = tcgen05 at every width,
+ *                          1 = CUDA-core cross-check; all pointers 16-byte aligned
  *   gfb_refiner_out_f32    out [B,OC,P] fp32 = w [OC][Cp] . act + bias   (out_conv on d.float(), OC <= 4)
- *   gfb_refiner_blocks_f16 the whole tail for d [B,C,G,G] -> out [B,out_dim,G,G], a batch chunk at a time so that the two
- *                          activation buffers stay in L2 over the nblocks blocks; weights = the packed blob
+ *   gfb_refiner_blocks_f16 the whole tail for d [B,C,G,G] -> out [B,out_dim,G,G] over two ping-pong activation buffers in the
+ *                          workspace (`chunk` batch elements at a time, 0 = all unless a buffer exceeds 1 GiB); weights = the packed blob
  *                          per block [wf 25*Cp f32][shift Cp f32][b2 Cp f32][w2 Cp*Cp f16], then [wout out_dim*Cp f32][bout 4 f32]
  *                          (gfnet_b200/refiner.py packs it from a ConvRefiner); chunk 0 = gfb_refiner_blocks_chunk.
  * gfb_flow_update_f32: the loop body model/network.py:265-274 for delta [B,3,G,G] = (dx, dy, d_certainty):

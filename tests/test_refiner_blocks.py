@@ -127,11 +127,12 @@ def test_dw5_bn_relu_kernel(c, G, b):
 
 
 @gpu
-@pytest.mark.parametrize("algo", [1, 0])
+@pytest.mark.parametrize("algo", [1, 0, 2])
 @pytest.mark.parametrize("cp,P", [(32, 1000), (80, 4096 + 37), (192, 128 * 300), (368, 5000), (432, 2048 + 5), (432, 128 * 700),
-                                  (256, 777), (16, 130), (512, 640)])
+                                  (256, 777), (16, 130), (512, 640), (48, 3333), (64, 70001), (96, 515), (80, 9), (32, 16 * 5000)])
 def test_pointwise_gemm(cp, P, algo):
-    """1x1 convolution as a GEMM: the tcgen05 kernel (algo 0) and the CUDA-core cross-check (algo 1) against torch."""
+    """1x1 convolution as a GEMM against torch: algo 0 = auto (streaming mma.sync kernel for Cp <= 96, tcgen05 above), 2 = the
+    tcgen05 kernel at every width, 1 = the CUDA-core cross-check."""
     from gfnet_b200 import refiner as RF
     g = torch.Generator(device="cuda").manual_seed(cp + P)
     act = torch.randn(P, cp, generator=g, device="cuda").half()

@@ -1,5 +1,6 @@
 """One small launch of every hot kernel (for compute-sanitizer): the rotated-order point kernel, the tcgen05 kernel (+ pre-pass),
-the mma.sync kernel, the refiner assemble kernel, the tcgen05 global match, the symmetric kde, top-k, the homography solver.
+the mma.sync kernel, the refiner assemble kernel, the tcgen05 global match, the symmetric kde, top-k, the homography solver,
+the refiner convolution tail.
 Usage: compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitize.py [names...]"""
 import os
 import sys
@@ -49,4 +50,26 @@ run("kde4_sym", lambda: gf.kde(pts, 0.1, half=False))
 key = torch.rand((2, 20000), generator=gen, device=dev)
 run("topk", lambda: gf.topk_desc(key, 5000))
 run("homography", lambda: gf.estimate_homography(pts, 448, 448, 448, 448))
+# refiner convolution tail: pack, depth-wise, 1x1 GEMM (tcgen05 at C = 177, mma.sync at C = 24 / 73), out_conv, glue
+from gfnet_b200 import refiner as RF
+
+
+def tail(c, G, algo=0):
+    torch.manual_seed(c)
+    blocks = [torch.nn.Sequential(torch.nn.Conv2d(c, c, 5, 1, 2, groups=c), torch.nn.BatchNorm2d(c), torch.nn.ReLU(inplace=True),
+                                  torch.nn.Conv2d(c, c, 1, 1, 0)).cuda().eval() for _ in range(2)]
+    rb = RF.RefinerBlocks(blocks, torch.nn.Conv2d(c, 3, 1, 1, 0).cuda().eval())
+    d = torch.randn((2, c, G, G), generator=gen, device=dev)
+    return lambda: rb(d, algo=algo)
+
+
+run("rb_tail_c177", tail(177, 24))
+run("rb_tail_c73", tail(73, 40))
+run("rb_tail_c24", tail(24, 48))
+run("rb_tail_c24_tc", tail(24, 48, algo=2))
+dl = torch.randn((2, 3, 32, 32), generator=gen, device=dev)
+fw, ce = torch.rand((2, 2, 32, 32), generator=gen, device=dev), torch.zeros((2, 1, 32, 32), device=dev)
+pre = torch.zeros_like(fw) + 1e-7
+run("flow_update", lambda: RF.flow_update(dl, fw, ce, pre, 8, 448, 448))
+run("upsample", lambda: RF.upsample_bilinear(fw, 64))
 print("done")
