@@ -398,7 +398,7 @@ def refiner_tail_run(synth, args, B, dev):
     random-init weights, times num_itr.  Scale 1 (no local correlation, model/network.py:139-153) included."""
     import torch
     from gfnet_b200 import refiner as RF
-    res, up = CONFIGS[args.config][0]
+    res, up, _ = synth.WORKLOADS[args.config]
     ddim = {16: 64, 8: 64, 4: 32, 2: 16, 1: 8}
     shapes = []
     for pi, u in enumerate((None, up) if up else (None,)):

@@ -436,33 +436,41 @@ __global__ void __launch_bounds__(PW_THREADS, 2) rb_pw_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// out_conv: fp32 1x1 convolution hidden -> OC (<= 4) on the fp16 activations, NCHW fp32 output.  L lanes per pixel.
-template <int L>
+// out_conv: fp32 1x1 convolution hidden -> OC (<= 4) on the fp16 activations, NCHW fp32 output.  Four lanes per pixel, each
+// reading 16-byte pieces of the NHWC row (a warp load covers 8 rows x 64 contiguous bytes), weights broadcast from shared memory.
 __global__ void __launch_bounds__(256) rb_out_kernel(const __half* __restrict__ act, const float* __restrict__ w /*[OC][Cp]*/,
                                                      const float* __restrict__ bias, float* __restrict__ out /*[B,OC,P]*/,
                                                      int B, int P, int Cp, int OC) {
-    const int lane = threadIdx.x & 31, sub = lane % L;
-    const long long pix = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * (32 / L) + lane / L;
+    extern __shared__ float ws[];                           // [4][Cp], rows >= OC zero
+    for (int i = threadIdx.x; i < 4 * Cp; i += 256) ws[i] = i < OC * Cp ? __ldg(w + i) : 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, t = lane & 3;
     const long long total = (long long)B * P;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (pix < total) {
-        const __half* row = act + (size_t)pix * Cp;
-        for (int c = 2 * sub; c < Cp; c += 2 * L) {
-            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(row + c));
+    // warp-uniform trip count (the shuffles below need the whole warp): 8 pixels per warp and round
+    for (long long w0 = ((long long)blockIdx.x * 256 + (threadIdx.x & ~31)) >> 2; w0 < total; w0 += ((long long)gridDim.x * 256) >> 2) {
+        const long long pix = w0 + (lane >> 2);
+        const bool ok = pix < total;
+        const __half* row = act + (size_t)(ok ? pix : 0) * Cp;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 8 * t; c < Cp && ok; c += 32) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(row + c));
+            const uint32_t hv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int o = 0; o < 4; ++o)
-                if (o < OC) acc[o] = fmaf(v.y, __ldg(w + o * Cp + c + 1), fmaf(v.x, __ldg(w + o * Cp + c), acc[o]));
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hv[e]));
+#pragma unroll
+                for (int o = 0; o < 4; ++o) acc[o] = fmaf(f.y, ws[o * Cp + c + 2 * e + 1], fmaf(f.x, ws[o * Cp + c + 2 * e], acc[o]));
+            }
         }
-    }
 #pragma unroll
-    for (int o = 0; o < 4; ++o)
-#pragma unroll
-        for (int m = L / 2; m > 0; m >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
-    if (pix < total && sub == 0) {
-        const long long b = pix / P, p = pix - b * P;
+        for (int o = 0; o < 4; ++o) {
+            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+            acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+        }
+        const long long bb = pix / P, p = pix - bb * P;
 #pragma unroll
         for (int o = 0; o < 4; ++o)
-            if (o < OC) out[((size_t)b * OC + o) * P + p] = acc[o] + __ldg(bias + o);
+            if (ok && o == t && o < OC) out[((size_t)bb * OC + o) * P + p] = acc[o] + __ldg(bias + o);
     }
 }
 
@@ -597,11 +605,9 @@ static int launch_pw(const __half* act, const __half* w2, const float* bias, __h
 }
 static int launch_out(const __half* act, const float* w, const float* bias, float* out, int B, int P, int Cp, int OC, cudaStream_t st) {
     const long long total = (long long)B * P;
-    if (Cp <= 32) {
-        rb_out_kernel<16><<<(unsigned)((total + 15) / 16), 256, 0, st>>>(act, w, bias, out, B, P, Cp, OC);
-    } else {
-        rb_out_kernel<32><<<(unsigned)((total + 7) / 8), 256, 0, st>>>(act, w, bias, out, B, P, Cp, OC);
-    }
+    const long long want = (total * 4 + 255) / 256;
+    const int grid = (int)min(want, (long long)148 * 8 * 4);          // grid-stride over the pixels: the weights are staged once per block
+    rb_out_kernel<<<grid, 256, 4 * Cp * sizeof(float), st>>>(act, w, bias, out, B, P, Cp, OC);
     return (int)cudaGetLastError();
 }
 
