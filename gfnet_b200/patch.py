@@ -12,7 +12,9 @@ from . import ops, matcher, refiner as _refiner
 def _blocks_on_device(module):
     """The packed convolution tail of a ConvRefiner, or None when the module is not the configuration the kernels cover
     (dw=True, kernel_size=5, BatchNorm2d in eval mode, fp16 / bf16 autocast): decided once per module and mode."""
-    key = (module.training, bool(module.amp))
+    w0, w1 = module.block1[0].weight, module.out_conv.weight          # load_state_dict / optimiser steps bump _version in place
+    key = (module.training, bool(module.amp), w0.data_ptr(), w1.data_ptr(),
+           None if w0.is_inference() else w0._version, None if w1.is_inference() else w1._version)
     cached = getattr(module, "_gfb_blocks_state", None)
     if cached is not None and cached[0] == key:
         return cached[1]
