@@ -212,13 +212,17 @@ def refiner_input(num_grid, x, y, flow, disp_weight, disp_bias, local_radius, sc
     the local correlation.  ``prepared`` / ``want_prepared``: the 64-channel scales run the tcgen05 kernel, whose feature
     pre-pass depends on ``x`` / ``y`` only; pass ``want_prepared=True`` on the first refiner iteration of a scale to get
     ``(d, handle)`` and hand ``prepared=handle`` (with ``out=d``) to the following ones (model/network.py:257-268).
+    ``local_radius=None``: no correlation channels (``corr_in_other=False``, :557-558).
     ``parts``: bit 0 = assemble, bit 1 = correlate (bench.py times the two launches separately), bit 2 = ``out[:, :c]`` already
     holds the grid features of this ``x`` (later iterations of a scale: they are not recomputed)."""
     xx = require_cuda_f32("x", x)
     yy = require_cuda_f32("y", y)
     fl = require_cuda_f32("flow", flow)
     B, c, hs, ws = (int(v) for v in xx.shape)
-    G, r = int(num_grid), int(local_radius)
+    no_corr = local_radius is None           # corr_in_other=False (the scale-1 refiner, :139-153): d = cat(grid_feature, x_hat, emb)
+    G, r = int(num_grid), 0 if no_corr else int(local_radius)
+    if no_corr:
+        parts &= ~2
     if yy.shape != xx.shape or fl.shape != (B, 2, G, G):
         raise ValueError("x / y must be [B,c,hs,ws] and flow [B,2,num_grid,num_grid]")
     w = require_cuda_f32("disp_weight", disp_weight.reshape(disp_weight.shape[0], -1).float())
@@ -226,7 +230,7 @@ def refiner_input(num_grid, x, y, flow, disp_weight, disp_bias, local_radius, sc
     dd = int(w.shape[0])
     if w.shape != (dd, 2) or bi.shape != (dd,):
         raise ValueError("disp_emb must be a 1x1 convolution 2 -> dd")
-    kk = (2 * r + 1) ** 2
+    kk = 0 if no_corr else (2 * r + 1) ** 2
     dtot = 2 * c + dd + kk
     if out is None:
         out = torch.empty((B, dtot, G, G), device=xx.device, dtype=torch.float32)

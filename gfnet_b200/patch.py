@@ -35,12 +35,12 @@ def _refiner_forward(original, blocks=True):
     activations like the reference's autocast, fp32 sums); otherwise the tail stays the reference's own modules under the
     reference's autocast."""
     def forward(self, num_grid, x, y, flow, scale_factor=1, logits=None):
-        if not (self.has_displacement_emb and self.corr_in_other and self.sample_mode == "bilinear" and x.is_cuda
+        if not (self.has_displacement_emb and self.sample_mode == "bilinear" and x.is_cuda
                 and x.dtype == torch.float32 and y.dtype == torch.float32 and flow.dtype == torch.float32):
             return original(self, num_grid, x, y, flow, scale_factor=scale_factor, logits=logits)
-        r = self.local_corr_radius
+        r = self.local_corr_radius if self.corr_in_other else None            # scale 1: no correlation channels (:557-558)
         d = ops.refiner_input(num_grid, x, y, flow, self.disp_emb.weight, self.disp_emb.bias, r, scale_factor)
-        local_corr = d[:, d.shape[1] - (2 * r + 1) ** 2:]
+        local_corr = d[:, d.shape[1] - (2 * r + 1) ** 2:] if r is not None else None
         rb = _blocks_on_device(self) if blocks else None
         if rb is not None:
             h = rb(d)
@@ -53,10 +53,13 @@ def _refiner_forward(original, blocks=True):
     return forward
 
 
-def patch(network_module, utils_local_correlation=None, utils_kde=None, refiner=True, refiner_blocks=True):
+def patch(network_module, utils_local_correlation=None, utils_kde=None, refiner=True, refiner_blocks=True, forward=False):
     """``patch(model.network)``; returns a dict of the originals so ``unpatch`` can restore them.  ``refiner=True`` also
     replaces the input assembly of ``ConvRefiner.forward``, ``refiner_blocks=True`` its convolution tail
-    (inference with the reference's autocast only, anything else keeps the reference's modules)."""
+    (SURVEY.md 8 f4; inference with the reference's autocast only, anything else keeps the reference's modules);
+    ``forward=True`` additionally replaces ``GFNet.forward`` by ``decoder.gfnet_forward`` (the reference's backbone, then the
+    whole refinement loop of model/network.py:224-287 on the device kernels: iterations of a scale share the refiner-input
+    buffer, flow update and between-scale upsampling are kernels)."""
     saved = {
         "refiner_forward": network_module.ConvRefiner.forward,
         "local_correlation": network_module.local_correlation,
@@ -64,6 +67,7 @@ def patch(network_module, utils_local_correlation=None, utils_kde=None, refiner=
         "corr_volume": network_module.GFNet.corr_volume,
         "pos_embed": network_module.GFNet.pos_embed,
         "sample": network_module.GFNet.sample,
+        "forward": network_module.GFNet.forward,
     }
     network_module.local_correlation = ops.local_correlation
     network_module.kde = ops.kde
@@ -75,6 +79,9 @@ def patch(network_module, utils_local_correlation=None, utils_kde=None, refiner=
     network_module.GFNet.sample = _sample
     if refiner:
         network_module.ConvRefiner.forward = _refiner_forward(saved["refiner_forward"], blocks=refiner_blocks)
+    if forward:
+        from .decoder import gfnet_forward
+        network_module.GFNet.forward = gfnet_forward(saved["forward"])
     if utils_local_correlation is not None:
         utils_local_correlation.local_correlation = ops.local_correlation
     if utils_kde is not None:
@@ -89,3 +96,5 @@ def unpatch(network_module, saved):
     network_module.GFNet.pos_embed = saved["pos_embed"]
     network_module.GFNet.sample = saved["sample"]
     network_module.ConvRefiner.forward = saved["refiner_forward"]
+    if "forward" in saved:
+        network_module.GFNet.forward = saved["forward"]
