@@ -372,12 +372,16 @@ def run_ours(args):
                 gpu_ref = gpu_reference_run(synth, args, dev)
             except Exception as exc:                   # secondary figure: never fail the bench line over it
                 gpu_ref = {"unavailable": repr(exc)[:200]}
-        tail = None
+        tail = full = None
         if world == 1 and not args.no_cpu_baseline:
             try:
                 tail = refiner_tail_run(synth, args, B, dev)
             except Exception as exc:
                 tail = {"unavailable": repr(exc)[:200]}
+            try:
+                full = full_decoder_run(synth, args, B, dev, hp, batch)
+            except Exception as exc:
+                full = {"unavailable": repr(exc)[:200]}
         line = {"metric": metric_name(args, synth), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": CONFIGS[args.config][1], "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(args, world, B, synth),
@@ -385,7 +389,7 @@ def run_ours(args):
                 "clocks": clocks, "gpu_launches": hp.kernel_launches(batch) * args.steps,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                         "overlap": "upload of step i+1 on a copy stream while step i computes (two device input sets)"},
-                "pipelined": pipelined, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": gpu_ref, "refiner_tail": tail,
+                "pipelined": pipelined, "roofline": roofline, "cpu_baseline": cpu, "reference_cuda": gpu_ref, "refiner_tail": tail, "full_decoder": full,
                 "ace_px_mean": float(out["err"].mean()), "solved": int(out["status"].sum())}
         print(json.dumps(line))
     if world > 1:
@@ -429,6 +433,72 @@ def refiner_tail_run(synth, args, B, dev):
     return {"what": "9 blocks of depth-wise 5x5 + batch norm + ReLU + 1x1 convolution, then out_conv, per scale / pass / iteration "
                     "(fp16 activations, fp32 sums); not part of `value`", "ms_per_step": tot_ms, "tflops": tot_flops / tot_ms * 1e-9,
             "launches_per_step": launches, "by_scale": rows}
+
+
+
+def full_decoder_run(synth, args, B, dev, hp, batch):
+    """Extra key: everything after the backbone for B pairs -- ``decoder.refine`` (coarse match, then per scale and iteration
+    refiner input + local correlation + convolution tail + flow update, upsampling; model/network.py:224-287) for the 448 pass and
+    the 560 upsample pass on random feature pyramids and random-init refiners of the reference's widths, plus the sparse tail
+    (post-process, sampling, kde, homography) of the bench step.  Not part of `value`."""
+    import torch
+    from gfnet_b200 import decoder
+    res, up, _ = synth.WORKLOADS[args.config]
+    ddim = {"16": 64, "8": 64, "4": 32, "2": 16, "1": 8}
+    chans = {"16": 64, "8": 64, "4": 32, "2": 16, "1": 8}
+    radius = {"16": 7, "8": 6, "4": 4, "2": 2, "1": 0}
+
+    class Refiner(torch.nn.Module):                      # the structure and widths of model/network.py:76-155, 444-531
+        def __init__(self, s):
+            super().__init__()
+            c, kk = chans[s], (2 * radius[s] + 1) ** 2 if s != "1" else 0
+            dim = 2 * c + ddim[s] + kk
+            mk = lambda: torch.nn.Sequential(torch.nn.Conv2d(dim, dim, 5, 1, 2, groups=dim), torch.nn.BatchNorm2d(dim),
+                                             torch.nn.ReLU(inplace=True), torch.nn.Conv2d(dim, dim, 1, 1, 0))
+            self.block1, self.hidden_blocks = mk(), torch.nn.Sequential(*[mk() for _ in range(8)])
+            self.out_conv, self.disp_emb = torch.nn.Conv2d(dim, 3, 1, 1, 0), torch.nn.Conv2d(2, ddim[s], 1, 1, 0)
+            self.local_corr_radius, self.corr_in_other, self.amp, self.amp_dtype = radius[s], s != "1", True, torch.float16
+
+    torch.manual_seed(0)
+    refiners = torch.nn.ModuleDict({s: Refiner(s) for s in ("16", "8", "4", "2", "1")}).to(dev).eval()
+    gen = torch.Generator(device=dev).manual_seed(7)
+
+    def pyramid(r, scales):
+        size = {"16": r // 14, "8": r // 8, "4": r // 4, "2": r // 2, "1": r}
+        return ({s: torch.randn((2 * B, chans[s], size[s], size[s]), generator=gen, device=dev) for s in scales},
+                {s: torch.randn((2 * B, chans[s], size[s], size[s]), generator=gen, device=dev) for s in scales})
+
+    g0 = res // 14
+    f0a, f1a = pyramid(res, ("16", "8", "4", "2", "1"))
+    grids_a = [g0, g0, 2 * g0, 4 * g0, 8 * g0]
+    if up:
+        f0b, f1b = pyramid(up, ("8", "4", "2", "1"))
+        gu = up // 14
+        grids_b = [gu, 2 * gu, 4 * gu, 8 * gu]
+
+    def run():
+        c = decoder.refine(f0a, f1a, refiners, grids_a, [NUM_ITR] * 5, res, res)
+        if up:
+            c = decoder.refine(f0b, f1b, refiners, grids_b, [NUM_ITR] * 4, up, up, scale_factor=up / res, upsample=True,
+                               pre_corresps=c["1"][NUM_ITR])
+        return c
+
+    run()
+    torch.cuda.synchronize(dev)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(2):
+        run()
+    e1.record()
+    for _ in range(2):
+        hp.run_back(batch)
+    e2.record()
+    torch.cuda.synchronize(dev)
+    dec_ms, back_ms = e0.elapsed_time(e1) / 2, e1.elapsed_time(e2) / 2
+    return {"what": "decoder.refine for the 448 pass + the 560 upsample pass (coarse match, refiner input + local correlation + "
+                    "convolution tail + flow update per scale and iteration, upsampling) + the sparse tail of the bench step; "
+                    "random pyramids, random-init refiners; not part of `value`",
+            "decoder_ms_per_step": dec_ms, "sparse_tail_ms_per_step": back_ms, "pairs_per_s": B / ((dec_ms + back_ms) / 1e3)}
 
 
 
