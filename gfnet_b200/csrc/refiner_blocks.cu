@@ -436,6 +436,141 @@ __global__ void __launch_bounds__(PW_THREADS, 2) rb_pw_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Fused block for the narrowest refiner (Cp = 32, scale 1: the most pixels): depth-wise 5x5 + batch norm + ReLU as in
+// rb_dw_kernel (16 lanes = the 16 channel pairs, two neighbouring strips per warp), then the 1x1 convolution of the same
+// pixels on mma.sync without the activations leaving the SM: two finished output rows of a warp (2 x 8 pixels x 32 channels)
+// go through a 1.25 KB warp-private shared-memory tile, from which every lane reads its A fragments as two 16-byte rows (the
+// k / n permutation of rb_pw_mma_kernel), eight MMAs, bias, and each lane stores 16 contiguous bytes of two output rows.
+constexpr int FU_PITCH = 80;      // bytes per pixel row of the tile: conflict-free 4-byte writes, 16-byte aligned reads
+
+__global__ void __launch_bounds__(DW_WARPS * 32, 3) rb_dwpw32_kernel(const __half* __restrict__ in, const float* __restrict__ wf,
+                                                                     const float* __restrict__ shift, const __half* __restrict__ w2,
+                                                                     const float* __restrict__ b2, __half* __restrict__ out,
+                                                                     int G, int th) {
+    constexpr int Cp = 32;
+    __shared__ uint2 wfrag[8][32];
+    __shared__ float bias_s[32];
+    __shared__ __align__(16) unsigned char tiles[DW_WARPS][16 * FU_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 8 * 32; i += DW_WARPS * 32) {
+        const int L = i & 31, f = i >> 5, j = f & 3, u = f >> 2;
+        const int co = 8 * ((L >> 2) >> 1) + 2 * j + ((L >> 2) & 1), ch = 8 * (L & 3) + 4 * u;
+        wfrag[f][L] = __ldg(reinterpret_cast<const uint2*>(w2 + co * Cp + ch));
+    }
+    if (threadIdx.x < 32) bias_s[threadIdx.x] = __ldg(b2 + threadIdx.x);
+    __syncthreads();
+
+    const int sx = lane >> 4, c = (lane & 15) * 2;
+    const int xw = (blockIdx.x * DW_WARPS + warp) * 8;                       // first pixel of the warp's two strips
+    const int x0 = xw + sx * 4, y0 = blockIdx.y * th, b = blockIdx.z;
+    const bool cok = x0 < G;
+    unsigned long long w[25];
+#pragma unroll
+    for (int t = 0; t < 25; ++t) w[t] = pack2(__ldg(wf + t * Cp + c), __ldg(wf + t * Cp + c + 1));
+    const float sh0 = __ldg(shift + c), sh1 = __ldg(shift + c + 1);
+    unsigned long long acc[5][4];
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[s][p] = 0ull;
+    const __half* inb = in + (size_t)b * G * G * Cp + c;
+    __half* outb = out + (size_t)b * G * G * Cp;
+    bool xok[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xok[i] = cok && x0 - 2 + i >= 0 && x0 - 2 + i < G;
+    unsigned char* tile = tiles[warp];
+    const int g = lane >> 2, t4 = lane & 3;
+
+    // 1x1 stage for output rows oA (tile rows 0-7) and oA + 1 (tile rows 8-15) of this warp's 8 pixels
+    auto pointwise = [&](int oA) {
+        __syncwarp();
+        const uint4 alo = *reinterpret_cast<const uint4*>(tile + g * FU_PITCH + t4 * 16);
+        const uint4 ahi = *reinterpret_cast<const uint4*>(tile + (g + 8) * FU_PITCH + t4 * 16);
+        float d[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[j][e] = 0.f;
+            const uint2 bu0 = wfrag[j][lane], bu1 = wfrag[4 + j][lane];
+            mma_m16n8k16_f16(d[j], alo.x, ahi.x, alo.y, ahi.y, bu0.x, bu0.y);
+            mma_m16n8k16_f16(d[j], alo.z, ahi.z, alo.w, ahi.w, bu1.x, bu1.y);
+        }
+        const float4 bl = *reinterpret_cast<const float4*>(bias_s + 8 * t4), bh = *reinterpret_cast<const float4*>(bias_s + 8 * t4 + 4);
+        uint4 o0, o1;
+        o0.x = f2_to_h2(d[0][0] + bl.x, d[0][1] + bl.y); o1.x = f2_to_h2(d[0][2] + bl.x, d[0][3] + bl.y);
+        o0.y = f2_to_h2(d[1][0] + bl.z, d[1][1] + bl.w); o1.y = f2_to_h2(d[1][2] + bl.z, d[1][3] + bl.w);
+        o0.z = f2_to_h2(d[2][0] + bh.x, d[2][1] + bh.y); o1.z = f2_to_h2(d[2][2] + bh.x, d[2][3] + bh.y);
+        o0.w = f2_to_h2(d[3][0] + bh.z, d[3][1] + bh.w); o1.w = f2_to_h2(d[3][2] + bh.z, d[3][3] + bh.w);
+        const int x = xw + g, yA = y0 + oA, yB = yA + 1;
+        if (x < G && yA < G) *reinterpret_cast<uint4*>(outb + ((size_t)yA * G + x) * Cp + 8 * t4) = o0;
+        if (x < G && oA + 1 < th && yB < G) *reinterpret_cast<uint4*>(outb + ((size_t)yB * G + x) * Cp + 8 * t4) = o1;
+        __syncwarp();
+    };
+
+    uint32_t raw[8];
+    const __half* row = inb + ((long long)(y0 - 2) * G + (x0 - 2)) * Cp;
+    const long long row_pitch = (long long)G * Cp;
+    auto load_row = [&](int j) {
+        const int iy = y0 - 2 + j;
+        const bool yok = iy >= 0 && iy < G && j < th + 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            raw[i] = 0u;
+            if (yok && xok[i]) raw[i] = __ldg(reinterpret_cast<const uint32_t*>(row + i * Cp));
+        }
+        row += row_pitch;
+    };
+    load_row(0);
+#pragma unroll 1
+    for (int base = 0; base < th + 4; base += 5) {
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const int j = base + s;
+            unsigned long long v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = h2_to_f2(raw[i]);
+            load_row(j + 1);
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky) {
+                const int slot = (s - ky + 5) % 5;
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) acc[slot][p] = fma2(w[ky * 5 + kx], v[p + kx], acc[slot][p]);
+            }
+            const int o = j - 4, slot = (s + 1) % 5;
+            if (o >= 0) {                                 // finished output row o -> tile rows (o & 1) * 8 + sx * 4 + p
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float2 a = unpack2(acc[slot][p]);
+                    *reinterpret_cast<uint32_t*>(tile + ((o & 1) * 8 + sx * 4 + p) * FU_PITCH + c * 2) =
+                        f2_to_h2(fmaxf(a.x + sh0, 0.f), fmaxf(a.y + sh1, 0.f));
+                }
+                if (o & 1) pointwise(o - 1);
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[slot][p] = 0ull;
+        }
+    }
+    if (th & 1) pointwise(th - 1);                         // odd strip height: the last row has no partner
+}
+
+static int launch_dwpw32(const __half* in, const float* wf, const float* shift, const __half* w2, const float* b2, __half* out,
+                         int B, int G, cudaStream_t st) {
+    const int xblocks = (G + 8 * DW_WARPS - 1) / (8 * DW_WARPS);
+    int th = DW_TH_MIN;
+    long long best = (long long)((G + th - 1) / th) * (th + 4);
+    for (int t = DW_TH_MIN + 5; t <= G + 4; t += 5) {
+        const int segs = (G + t - 1) / t;
+        if ((long long)xblocks * segs * B < 2 * 3 * 148) break;
+        if ((long long)segs * (t + 4) < best) { best = (long long)segs * (t + 4); th = t; }
+    }
+    dim3 grid(xblocks, (G + th - 1) / th, B);
+    rb_dwpw32_kernel<<<grid, DW_WARPS * 32, 0, st>>>(in, wf, shift, w2, b2, out, G, th);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // out_conv: fp32 1x1 convolution hidden -> OC (<= 4) on the fp16 activations, NCHW fp32 output.  Four lanes per pixel, each
 // reading 16-byte pieces of the NHWC row (a warp load covers 8 rows x 64 contiguous bytes), weights broadcast from shared memory.
 __global__ void __launch_bounds__(256) rb_out_kernel(const __half* __restrict__ act, const float* __restrict__ w /*[OC][Cp]*/,
@@ -696,6 +831,11 @@ extern "C" int gfb_refiner_blocks_f16(const float* d, const void* weights, float
             const float* shift = wf + 25 * Cp;
             const float* b2 = shift + Cp;
             const __half* w2 = reinterpret_cast<const __half*>(b2 + Cp);
+            if (Cp == 32 && algo == 0) {          // scale 1: depth-wise and 1x1 stages in one kernel, buffers swap roles
+                RB_TRY(launch_dwpw32(h, wf, shift, w2, b2, a, nb, G, st));
+                __half* tmp = h; h = a; a = tmp;
+                continue;
+            }
             RB_TRY(launch_dw(h, wf, shift, a, nb, G, Cp, st));
             RB_TRY(launch_pw(a, w2, b2, h, (long long)nb * P, Cp, algo, st));
         }
