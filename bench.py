@@ -373,7 +373,7 @@ def run_ours(args):
             except Exception as exc:                   # secondary figure: never fail the bench line over it
                 gpu_ref = {"unavailable": repr(exc)[:200]}
         tail = full = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_extras:
             try:
                 tail = refiner_tail_run(synth, args, B, dev)
             except Exception as exc:
@@ -511,6 +511,7 @@ def main():
     ap.add_argument("--config", default="visir448", choices=sorted(CONFIGS))
     ap.add_argument("--pairs-per-gpu", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the refiner_tail / full_decoder extra keys (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else min(args.steps, 6)     # ~6 s of CPU work per pair

@@ -89,6 +89,28 @@ def test_flow_update_port_zero_rule():
     assert float(disp2.abs().max()) == 0 and torch.equal(f2, f1)
 
 
+def test_no_cpu_path():
+    """The product path has no CPU fallback: CPU tensors / modules raise."""
+    from gfnet_b200 import refiner as RF
+    blocks, oc = _make_blocks(16, nblocks=1)
+    with pytest.raises(RuntimeError):
+        RF.RefinerBlocks(blocks, oc)
+    with pytest.raises(RuntimeError):
+        RF.flow_update(torch.zeros(1, 3, 4, 4), torch.zeros(1, 2, 4, 4), torch.zeros(1, 1, 4, 4), torch.zeros(1, 2, 4, 4), 8, 448, 448)
+    with pytest.raises(RuntimeError):
+        RF.upsample_bilinear(torch.zeros(1, 2, 4, 4), 8)
+    with pytest.raises(RuntimeError):
+        RF.pack_nhwc_f16(torch.zeros(1, 3, 4, 4))
+
+
+def test_decoder_module_imports_and_signature():
+    import inspect
+    from gfnet_b200 import decoder
+    sig = inspect.signature(decoder.gfnet_forward(lambda *a, **k: None))
+    assert list(sig.parameters)[:3] == ["self", "batch", "symmetric"]         # GFNet.forward, model/network.py:203
+    assert {"upsample", "scale_factor", "pre_corresps"} <= set(sig.parameters)
+
+
 # ---- GPU ---------------------------------------------------------------------------------------------------------------
 gpu = pytest.mark.gpu
 

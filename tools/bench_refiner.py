@@ -1,6 +1,7 @@
 """Kernel bench of the refiner convolution tail at the pipeline's shapes: ms per call, useful TFLOP/s,
-fraction of the measured bf16 peak, the HBM floor of the fused formulation, and torch's own modules (cuDNN / cuBLAS under fp16
-autocast = what the reference runs on a GPU) on the same device beside it.
+fraction of the measured bf16 peak, the HBM floor of the fused formulation, torch's own modules (cuDNN / cuBLAS under fp16
+autocast = what the reference runs on a GPU) on the same device and the same modules on the box's host cores (fp32 = the
+reference's CPU path, one batch element) beside it.
 
     python tools/bench_refiner.py [--b 64] [--out gpurun_out/refiner_bench.json]
 """
@@ -45,6 +46,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--out", default="gpurun_out/refiner_bench.json")
     ap.add_argument("--torch", type=int, default=1)
+    ap.add_argument("--cpu", type=int, default=1)
     a = ap.parse_args()
     peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
     rows, tot = [], {"ms": 0.0, "flops": 0.0, "torch_ms": 0.0}
@@ -65,6 +67,18 @@ def main():
                "launches": rb.launches(a.b, G), "chunk": int(RF.lib.gfb_refiner_blocks_chunk(a.b, c, G)),
                "dw_ms_b8": ms_dw, "dw_GBps_l2": 2 * 8 * G * G * cp * 2 / ms_dw * 1e-6,
                "pw_ms_b8": ms_pw, "pw_tflops": 2 * 8 * G * G * cp * cp / ms_pw * 1e-9}
+        if a.cpu:      # the reference's CPU path (fp32: its autocast is off on the CPU, utils/utils.py:306-320), one batch element
+            import copy
+            import time
+            cseq, coc = copy.deepcopy(torch.nn.Sequential(*blocks)).cpu(), copy.deepcopy(oc).cpu()
+            dc = d[:1].cpu()
+            with torch.no_grad():
+                coc(cseq(dc.clone()))
+                t0 = time.perf_counter()
+                coc(cseq(dc.clone()))
+                row["cpu_fp32_ms_b1"] = (time.perf_counter() - t0) * 1e3
+            row["cpu_threads"] = torch.get_num_threads()
+            row["gpu_over_cpu_per_element"] = row["cpu_fp32_ms_b1"] / (ms / a.b)
         if a.torch:
             seq = torch.nn.Sequential(*blocks)
 
