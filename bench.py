@@ -63,9 +63,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, timed=None):
+        """Median SM clock over every sample between start() and now -- the sampler runs from before the warm-up to the end of
+        the end-to-end loop, all of it under load (the timed region alone is ~50 ms: one 50 ms sample at best) -- plus how many
+        of the samples fell inside ``timed = (t0, t1)`` (host clock)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -74,7 +77,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        self.in_timed = sum(1 for (t, _) in self.rows if timed and timed[0] <= t <= timed[1] + 0.05)
+        for (_, r) in self.rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -84,7 +88,9 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_in_timed_region": self.in_timed,
+                "window": "warm-up + timed steps + pipelined steps + end-to-end loop (all under load), 50 ms period",
+                "reasons": sorted(reasons)}
 
 
 def metric_name(args, synth):
@@ -221,12 +227,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)                # nvidia-smi needs ~0.2 s before its first sample
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
     hp.timing = []                     # CUDA-event pairs around every local_correlation launch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -239,7 +246,7 @@ def run_ours(args):
     t_host = time.perf_counter() - t_host0          # host time to ISSUE the steps (no sync): launch-bound if ~ device time
     barrier()
     assert all_rows.shape[0] == world
-    clocks = sampler.stop() if rank == 0 else None
+    t_timed = (t_host0, time.perf_counter())
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     lc_ms = sum(a.elapsed_time(b) for (_, a, b) in hp.timing)
     lc_by_scale = {}
@@ -338,6 +345,7 @@ def run_ours(args):
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_value = B * world * e2e_steps / (float(ems.item()) / 1e3)
     del batch_b, sets
+    clocks = sampler.stop(t_timed) if rank == 0 else None
 
     if rank == 0:
         peaks, src = measured_peaks()
