@@ -18,7 +18,7 @@ EXPORTS = [
     "gfb_debug_local_corr_v2_counters", "gfb_debug_local_corr_tc2_f32", "gfb_debug_local_corr_pt_f32",
     "gfb_global_match_f32", "gfb_pos_embed_f32", "gfb_kde_f32", "gfb_kde_sym_workspace_bytes", "gfb_kde_sym_f32", "gfb_match_postprocess_f32",
     "gfb_sample_keys_f32", "gfb_balance_keys_f32", "gfb_gather_matches_f32", "gfb_topk_workspace_bytes",
-    "gfb_refiner_pack_f16", "gfb_refiner_dw5_f16", "gfb_refiner_pw_f16", "gfb_refiner_out_f32", "gfb_refiner_blocks_weight_bytes",
+    "gfb_debug_refiner_dw5_planar_f16", "gfb_refiner_pack_f16", "gfb_refiner_dw5_f16", "gfb_refiner_pw_f16", "gfb_refiner_out_f32", "gfb_refiner_blocks_weight_bytes",
     "gfb_refiner_blocks_chunk", "gfb_refiner_blocks_workspace_bytes", "gfb_refiner_blocks_f16", "gfb_flow_update_f32",
     "gfb_upsample_bilinear_f32",
     "gfb_topk_desc_f32", "gfb_homography_workspace_bytes", "gfb_homography_f32", "gfb_homography_cv_f32", "gfb_corner_error_f64",
@@ -60,6 +60,7 @@ def _load():
     lib.gfb_local_corr_cat_f32.argtypes = [vp, i32, vp, vp] + [i32] * 9 + [vp, sz, vp]
     lib.gfb_refiner_pack_f16.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.gfb_refiner_dw5_f16.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.gfb_debug_refiner_dw5_planar_f16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.gfb_refiner_pw_f16.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
     lib.gfb_refiner_out_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.gfb_refiner_blocks_weight_bytes.restype = sz

@@ -436,6 +436,115 @@ __global__ void __launch_bounds__(PW_THREADS, 2) rb_pw_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Depth-wise 5x5 on the tensor cores, channel-planar fp16 (EXPERIMENT): per plane and ky the convolution along
+// x is a banded (Toeplitz) 16 x 8 matrix T_ky[k][n] = w[ky][k - n], so 16 output rows x 8 output pixels are five
+// mma.sync.m16n8k16 with A_ky[m][k] = in[y0 + m + ky - 2][x0 - 2 + k] read straight from the plane (a lane's 4-byte loads are
+// its A fragments; neighbouring 8-pixel tiles share half of them) and T_ky a per-channel constant in registers.
+// A warp = 16 rows x 32 pixels of one plane: 50 loads, 20 MMAs, 8 stores for 512 outputs (the FFMA2 kernel issues ~500
+// instructions for as many).  Taps are rounded to fp16 (as the reference's autocast does), sums are fp32.
+constexpr int DWM_PITCH = 36;      // words per staged row (48 pixels + pad): pitch = 4 (mod 32) -> conflict-free fragment reads
+constexpr int DWM_ROWS = 20;       // 16 output rows + 4 halo rows per step
+
+// A warp owns a 32-pixel-wide column strip of one plane and walks it downwards in steps of 16 rows: the B fragments are built
+// once, every step stages 20 rows x 48 pixels (16-byte chunks, prefetched into registers one step ahead) in a warp-private
+// shared-memory tile, reads its 50 A-fragment words, issues 20 MMAs and stores 16 x 32 outputs: ~135 instructions per 512
+// outputs.  No block-wide barrier.
+__global__ void __launch_bounds__(128) rb_dwm_kernel(const __half* __restrict__ in, const float* __restrict__ wf,
+                                                     const float* __restrict__ shift, __half* __restrict__ out,
+                                                     int C, int Cp, int G, int seg) {
+    __shared__ __align__(16) uint32_t tiles[4][DWM_ROWS * DWM_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int plane = blockIdx.z, c = plane % C;
+    const int x0 = (blockIdx.x * 4 + warp) * 32;
+    if (x0 >= G) return;
+    const int ys = blockIdx.y * seg, ye = min(G, ys + seg);
+    const __half* ip = in + (size_t)plane * G * G;
+    __half* op = out + (size_t)plane * G * G;
+    uint32_t* tile = tiles[warp];
+    uint32_t b0[5], b1[5];
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+        float e[4];
+        const int d[4] = {2 * t - g, 2 * t + 1 - g, 2 * t + 8 - g, 2 * t + 9 - g};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = (d[i] >= 0 && d[i] <= 4) ? __ldg(wf + (ky * 5 + d[i]) * Cp + c) : 0.f;
+        b0[ky] = f2_to_h2(e[0], e[1]);
+        b1[ky] = f2_to_h2(e[2], e[3]);
+    }
+    const float sh = __ldg(shift + c);
+    // the lane's four 16-byte chunks of a step: chunk index lane + 32 q -> (row, chunk of the row); 120 chunks per step
+    int ry[4], cx[4];
+    bool cok[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int idx = lane + 32 * q;
+        ry[q] = idx / 6;
+        const int ch = idx - ry[q] * 6;
+        cx[q] = x0 - 8 + 8 * ch;
+        cok[q] = idx < DWM_ROWS * 6 && cx[q] >= 0 && cx[q] < G;
+    }
+    // per-lane pointers, advanced by 16 rows per step (no 64-bit address arithmetic inside the loop)
+    const uint4* lp[4];
+    uint32_t* sp[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        lp[q] = reinterpret_cast<const uint4*>(ip + ((long long)(ys - 2 + ry[q]) * G + cx[q]));
+        sp[q] = tile + ry[q] * DWM_PITCH + ((cx[q] - x0 + 8) >> 1);
+    }
+    const long long step16 = (long long)2 * G;                 // 16 rows in uint4 units (8 halves each)
+    uint4 pre[4];
+    auto fetch = [&](int y0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int y = y0 - 2 + ry[q];
+            pre[q] = make_uint4(0u, 0u, 0u, 0u);
+            if (cok[q] && y >= 0 && y < G) pre[q] = __ldg(lp[q]);
+            lp[q] += step16;
+        }
+    };
+    fetch(ys);
+    const uint32_t* fr = tile + g * DWM_PITCH + 3 + t;         // the lane's fragment words: fr[row * PITCH + 4 j]
+    for (int y0 = ys; y0 < ye; y0 += 16) {
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (lane + 32 * q < DWM_ROWS * 6) *reinterpret_cast<uint4*>(sp[q]) = pre[q];
+        __syncwarp();
+        if (y0 + 16 < ye) fetch(y0 + 16);
+        // staged rows g + ky (i = ky) and g + 8 + ky (i = 5 + ky); word 3 + 4 j + t = pixels x0 - 2 + 8 j + 2 t, + 1
+        uint32_t r[10][5];
+#pragma unroll
+        for (int i = 0; i < 10; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) r[i][j] = fr[(i < 5 ? i : i + 3) * DWM_PITCH + 4 * j];
+        float d[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) d[n][e] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)                          // four independent accumulator chains per ky
+#pragma unroll
+            for (int n = 0; n < 4; ++n) mma_m16n8k16_f16(d[n], r[ky][n], r[5 + ky][n], r[ky][n + 1], r[5 + ky][n + 1], b0[ky], b1[ky]);
+        // the 16 x 32 outputs go back through the (now free) tile so that every lane stores two 16-byte row pieces: 16 store
+        // wavefronts per step instead of 64 for 4-byte fragment stores (the LSU data pipe is what bounds this kernel)
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            tile[g * DWM_PITCH + 4 * n + t] = f2_to_h2(fmaxf(d[n][0] + sh, 0.f), fmaxf(d[n][1] + sh, 0.f));
+            tile[(g + 8) * DWM_PITCH + 4 * n + t] = f2_to_h2(fmaxf(d[n][2] + sh, 0.f), fmaxf(d[n][3] + sh, 0.f));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int id = lane + 32 * q, orow = id >> 2, c4 = id & 3;
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + orow * DWM_PITCH + 4 * c4);
+            if (y0 + orow < ye && x0 + 8 * c4 < G) *reinterpret_cast<uint4*>(op + ((long long)(y0 + orow) * G + x0 + 8 * c4)) = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Fused block for the narrowest refiner (Cp = 32, scale 1: the most pixels): depth-wise 5x5 + batch norm + ReLU as in
 // rb_dw_kernel (16 lanes = the 16 channel pairs, two neighbouring strips per warp), then the 1x1 convolution of the same
 // pixels on mma.sync without the activations leaving the SM: two finished output rows of a warp (2 x 8 pixels x 32 channels)
@@ -769,6 +878,17 @@ extern "C" int gfb_refiner_dw5_f16(const void* in, const float* wf, const float*
                                    gfb_stream_t stream) {
     GFB_CHECK_ARG(in && wf && shift && out && in != out && B > 0 && B <= 65535 && G > 0 && Cp > 0 && Cp % 16 == 0);
     return launch_dw((const __half*)in, wf, shift, (__half*)out, B, G, Cp, gfb_cu(stream));
+}
+
+// EXPERIMENT: channel-planar depth-wise stage on the tensor cores; in / out [B*C][G][G] fp16, G % 8 == 0
+extern "C" int gfb_debug_refiner_dw5_planar_f16(const void* in, const float* wf, const float* shift, void* out, int B, int C, int Cp,
+                                                int G, gfb_stream_t stream) {
+    GFB_CHECK_ARG(in && wf && shift && out && in != out && B > 0 && C > 0 && Cp >= C && G > 0 && G % 8 == 0);
+    GFB_CHECK_ARG((long long)B * C <= 65535);
+    const int seg = G >= 256 ? 128 : ((G + 15) / 16) * 16;          // rows per block: whole columns unless the plane is tall
+    dim3 grid((G + 127) / 128, (G + seg - 1) / seg, B * C);
+    rb_dwm_kernel<<<grid, 128, 0, gfb_cu(stream)>>>((const __half*)in, wf, shift, (__half*)out, C, Cp, G, seg);
+    GFB_LAUNCH_RESULT();
 }
 
 extern "C" int gfb_refiner_pw_f16(const void* act, const void* w2, const float* bias, void* out, long long P, int Cp, int algo,

@@ -152,6 +152,9 @@ int gfb_local_corr_cat_f32(float* d, int Dtot, const float* f1, const float* flo
 int gfb_refiner_pack_f16(const float* d, void* out, int B, int C, int P, gfb_stream_t stream);
 int gfb_refiner_dw5_f16(const void* in, const float* wf, const float* shift, void* out, int B, int G, int Cp,
                         gfb_stream_t stream);
+/* experiment: the depth-wise stage on channel-planar fp16 [B*C][G][G] as banded MMAs */
+int gfb_debug_refiner_dw5_planar_f16(const void* in, const float* wf, const float* shift, void* out, int B, int C, int Cp,
+                                     int G, gfb_stream_t stream);
 int gfb_refiner_pw_f16(const void* act, const void* w2, const float* bias, void* out, long long P, int Cp, int algo,
                        gfb_stream_t stream);
 int gfb_refiner_out_f32(const void* act, const float* w, const float* bias, float* out, int B, int P, int Cp, int OC,

@@ -149,6 +149,26 @@ def test_dw5_bn_relu_kernel(c, G, b):
 
 
 @gpu
+@pytest.mark.parametrize("c,G,b", [(24, 256, 1), (73, 128, 2), (24, 40, 3), (177, 64, 1), (5, 8, 2)])
+def test_dw5_planar_tensor_core_experiment(c, G, b):
+    """The channel-planar depth-wise stage as banded MMAs (gfb_debug_refiner_dw5_planar_f16) against torch in
+    float64: taps rounded to fp16 like the reference's autocast, fp32 sums, one fp16 rounding of the output."""
+    from gfnet_b200 import refiner as RF
+    from gfnet_b200._lib import lib, check, ptr, stream_ptr
+    cp = RF.pad16(c)
+    g = torch.Generator(device="cuda").manual_seed(c + G)
+    w = torch.randn((c, 25), generator=g, device="cuda") * 0.2
+    wf = torch.zeros((25, cp), device="cuda"); wf[:, :c] = w.t()
+    shift = torch.zeros(cp, device="cuda"); shift[:c] = torch.randn(c, generator=g, device="cuda") * 0.1
+    x = torch.randn((b, c, G, G), generator=g, device="cuda").half().contiguous()
+    out = torch.full_like(x, float("nan"))
+    check(lib.gfb_debug_refiner_dw5_planar_f16(ptr(x), ptr(wf), ptr(shift), ptr(out), b, c, cp, G, stream_ptr("cuda")), "dw planar")
+    ref = F.relu(F.conv2d(x.double(), w.double().reshape(c, 1, 5, 5), shift[:c].double(), 1, 2, 1, c))
+    assert bool(torch.isfinite(out.float()).all())
+    assert float((out.double() - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-4
+
+
+@gpu
 @pytest.mark.parametrize("algo", [1, 0, 2])
 @pytest.mark.parametrize("cp,P", [(32, 1000), (80, 4096 + 37), (192, 128 * 300), (368, 5000), (432, 2048 + 5), (432, 128 * 700),
                                   (256, 777), (16, 130), (512, 640), (48, 3333), (64, 70001), (96, 515), (80, 9), (32, 16 * 5000)])
