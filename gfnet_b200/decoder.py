@@ -65,6 +65,40 @@ def refine(features0, features1, conv_refiner, num_grid, num_itr, H0, W0, *, sca
     return corresps
 
 
+class GraphedRefine:
+    """``refine`` for fixed shapes captured in a CUDA graph: one replay instead of ~400 kernel launches issued from Python per
+    pass -- what matters at the reference's own operating point of ONE pair per call (test.py), where the eager loop is bound by
+    host launch overhead, not by the GPU.  Inputs are copied into static buffers, the returned ``corresps`` tensors are static too
+    (valid until the next call)."""
+
+    def __init__(self, features0, features1, conv_refiner, num_grid, num_itr, H0, W0, *, scale_factor=1, upsample=False,
+                 pre_corresps=None, zero_rule=True):
+        self.f0 = {s: t.detach().clone() for s, t in features0.items()}
+        self.f1 = {s: t.detach().clone() for s, t in features1.items()}
+        self.pre = None if pre_corresps is None else {k: v.detach().clone() for k, v in pre_corresps.items()}
+        args = (self.f0, self.f1, conv_refiner, list(num_grid), list(num_itr), H0, W0)
+        kw = dict(scale_factor=scale_factor, upsample=upsample, pre_corresps=self.pre, zero_rule=zero_rule)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up outside the capture: packs weights, sets kernel attributes
+            for _ in range(2):
+                refine(*args, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = refine(*args, **kw)
+
+    def __call__(self, features0, features1, pre_corresps=None):
+        for s in self.f0:
+            self.f0[s].copy_(features0[s])
+            self.f1[s].copy_(features1[s])
+        if self.pre is not None:
+            for k in self.pre:
+                self.pre[k].copy_(pre_corresps[k])
+        self.graph.replay()
+        return self.out
+
+
 def gfnet_forward(original):
     """Replacement for ``GFNet.forward`` (model/network.py:203-287): the reference's own ``extract_features``, then ``refine``.
     Refiners in training mode, CPU tensors or visualisation requests go to the original."""
@@ -87,4 +121,4 @@ def gfnet_forward(original):
     return forward
 
 
-__all__ = ["refine", "refiner_delta", "gfnet_forward"]
+__all__ = ["refine", "refiner_delta", "gfnet_forward", "GraphedRefine"]

@@ -146,3 +146,26 @@ def test_gfnet_forward_upsample_pass():
     c0, c1 = _run_both(ref, self, batch, upsample=True, scale_factor=1.25, pre_corresps=pre)
     assert list(c0.keys()) == list(c1.keys()) == ["8", "4", "2", "1"]
     _compare(c0, c1, "GFNet.forward upsample pass", tol_flow=1e-4, tol_cert=2e-2)
+
+
+def test_graphed_refine_is_identical_to_eager():
+    """decoder.GraphedRefine (the loop captured in a CUDA graph) replays bit-identical results, also after new inputs."""
+    from gfnet_b200 import decoder
+    ref = R.load_reference()
+    self = _stand_in(ref, 224, [2, 2, 2, 2, 2], seed=13)
+    fq, fs = self.extract_features(None)
+    f0 = {s: torch.cat((fq[s], fs[s]), 0).contiguous() for s in fq}
+    f1 = {s: torch.cat((fs[s], fq[s]), 0).contiguous() for s in fq}
+    with torch.inference_mode():
+        graphed = decoder.GraphedRefine(f0, f1, self.conv_refiner, self.num_grid, self.num_itr, 224, 224)
+        for trial in range(2):
+            if trial == 1:                                   # other inputs through the same graph
+                f0 = {s: t.flip(0).contiguous() for s, t in f0.items()}
+                f1 = {s: t.flip(0).contiguous() for s, t in f1.items()}
+            eager = decoder.refine(f0, f1, self.conv_refiner, self.num_grid, self.num_itr, 224, 224)
+            out = graphed(f0, f1)
+            torch.cuda.synchronize()
+            for s in eager:
+                for it in eager[s]:
+                    assert torch.equal(eager[s][it]["flow"], out[s][it]["flow"])
+                    assert torch.equal(eager[s][it]["certainty"], out[s][it]["certainty"])
