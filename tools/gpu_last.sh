@@ -9,7 +9,7 @@ timeout 600 python bench.py --config map224 --steps 10 --warmup 3 --no-cpu-basel
 timeout 600 python bench.py --config map672 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_map672_1gpu.json 2>> gpurun_out/final_bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>> gpurun_out/final_bench.err
 timeout 600 python tools/bench_refiner.py --b 64 --out gpurun_out/r2_refiner_bench.json > gpurun_out/rb_bench.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:rb_dwpw32 --launch-skip 2 --launch-count 1 -f -o gpurun_out/r2_full_dwpw_s1 python tools/profile_refiner.py --shape p1_s1 --b 64 > gpurun_out/ncu_dwpw_s1.log 2>&1
+
 cat gpurun_out/final_gpu_tests.log gpurun_out/final_smoke.log; tail -1 gpurun_out/rb_bench.log | cut -c1-400; tail -3 gpurun_out/final_bench.err
 for f in visir448 map224 map672; do python - "$f" <<'PY'
 import json, sys
